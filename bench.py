@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of BASELINE.json: coded bits/s of LDPC5G BP decoding, n=8448 (k=4224), 20
+iterations, batch 4096 per GPU (weak scaling over 1/2/4/8 B200; one process per GPU, NCCL all-reduce of the four
+int64 error counters per step, as sim_ber's replicas do: /root/reference/src/sionna/phy/utils/misc.py:614-655).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--cn-update boxplus-phi|minsum|...] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one LDPC5GDecoder call on a [4096, 8448] fp32 logit tensor resident in HBM + error counting (+ the
+counter all-reduce for N > 1). Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_INFO, N_CODE, BATCH, NUM_ITER = 4224, 8448, 4096, 20
+EBNO_DB = 2.0
+# SURVEY.md 8(d) / BASELINE.md: algorithmic bytes per codeword for flooding BP, one fp32 message per edge read +
+# written once per iteration, one channel LLR read per VN per iteration, plus compulsory I/O.
+E_EDGES, N_VNS = 40320, 8832
+ALG_BYTES_PER_CW = NUM_ITER * (8 * E_EDGES + 4 * N_VNS) + 4 * N_CODE + 4 * K_INFO      # 7 208 448
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(seed, batch, device=None):
+    """Seeded synthetic channel logits for the all-zero codeword (a valid codeword of the linear code) sent with
+    the reference's BPSK-equivalent mapping over AWGN at Eb/N0 = 2 dB: logit = log p(1)/p(0) = 4 y / no with
+    y = -1 + w. Decoder throughput is data independent (no early stopping, decoding.py:105-107)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    no = 1.0 / (10 ** (EBNO_DB / 10) * (K_INFO / N_CODE))
+    y = -1.0 + rng.standard_normal((batch, N_CODE), dtype=np.float32) * np.float32(np.sqrt(no / 2))
+    return (np.float32(4.0 / no) * y).astype(np.float32)
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores. TensorFlow (the reference's backend) is not
+    installable offline, so this times the CPU restatement (oracle/, libm math, all host threads) on a bounded
+    sample of the same workload: SAMPLE codewords of the [4096, 8448] batch per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import ldpc as O
+    cores = os.cpu_count() or 1
+    sample = max(cores * 2, 32)
+    enc = O.LDPC5GEncoderRef(K_INFO, N_CODE)
+    dec = O.LDPC5GDecoderRef(enc, cn_update=args.cn_update, num_iter=NUM_ITER)
+    llr = make_inputs(1234, sample)
+    for _ in range(args.warmup):
+        dec(llr[:cores], num_threads=cores)
+    t0 = time.perf_counter()
+    errs = 0
+    for _ in range(args.steps):
+        u_hat = dec(llr, num_threads=cores)
+        errs += int(u_hat.sum())
+    dt = time.perf_counter() - t0
+    val = sample * N_CODE * args.steps / dt
+    line = {"metric": "coded bits/s, LDPC5G n=8448 k=4224 BP-20 decode", "value": val, "unit": "coded bits/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LDPC5GDecoder(LDPC5GEncoder(4224,8448)) {args.cn_update} 20 it, "
+                                   f"{sample}-codeword sample of the batch-4096 workload per step"},
+            "cpu_baseline": {"value": val, "unit": "coded bits/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} codewords/step x {args.steps} steps, oracle/ldpc_bp_ref.c libm mode, "
+                                       f"OpenMP {cores} threads (TensorFlow reference not installable offline)"},
+            "e2e": {"value": val, "unit": "coded bits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cn-update", default="boxplus-phi",
+                    choices=["boxplus-phi", "boxplus", "minsum", "offset-minsum"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="codewords for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sionna_b200 import _lib
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "--gpus must match the torchrun world size"
+
+    enc = LDPC5GEncoder(K_INFO, N_CODE)
+    dec = LDPC5GDecoder(enc, cn_update=args.cn_update, num_iter=NUM_ITER, hard_out=True, return_infobits=True)
+    assert dec.on_chip and dec.num_edges == E_EDGES and dec.num_vns == N_VNS
+
+    # two distinct input sets (2 x 138 MB > 126 MB L2), alternated between steps: nothing the kernel reads from
+    # HBM can be an L2 hit left over from the previous step
+    h_in = [torch.from_numpy(make_inputs(100 + 1000 * rank + i, BATCH)).pin_memory() for i in range(2)]
+    d_in = [h.to(dev) for h in h_in]
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)     # bit errors, block errors, bits, blocks
+
+    def count(u_hat):
+        # all-zero codeword was sent: every 1 is a bit error (utils/metrics.py:94-144 semantics)
+        e = u_hat != 0
+        counters[0] += e.sum()
+        counters[1] += e.any(dim=-1).sum()
+        counters[2] += u_hat.numel()
+        counters[3] += u_hat.shape[0]
+
+    def step(i):
+        u_hat = dec(d_in[i & 1])
+        count(u_hat)
+        if world > 1:
+            dist.all_reduce(counters_step.copy_(counters), op=dist.ReduceOp.SUM)
+        return u_hat
+
+    counters_step = torch.zeros_like(counters)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+
+    # ---- kernel-only timing for the roofline: CUDA events on the launching stream around the decode call ------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    t_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        u_hat = dec(d_in[i & 1])
+        ev[i][1].record()
+        launches += _lib.lib().sb_ldpc_last_launch_count()
+        count(u_hat)
+        if world > 1:
+            dist.all_reduce(counters_step.copy_(counters), op=dist.ReduceOp.SUM)
+    t_stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = t_start.elapsed_time(t_stop)
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * BATCH * N_CODE * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: H2D of the logits, decode, D2H of the bits ------
+    h_out = torch.empty((BATCH, K_INFO), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        h_out.copy_(dec(h_in[i & 1].to(dev, non_blocking=True)), non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        x = h_in[i & 1].to(dev, non_blocking=True)
+        h_out.copy_(dec(x), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * BATCH * N_CODE * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = ALG_BYTES_PER_CW * BATCH / (kern_ms * 1e-3) / 1e9
+        c = counters.cpu().tolist()
+        line = {
+            "metric": "coded bits/s, LDPC5G n=8448 k=4224 BP-20 decode", "value": value, "unit": "coded bits/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: LDPC5GDecoder(LDPC5GEncoder(4224,8448)), cn_update={args.cn_update}, "
+                                   f"20 BP iterations, batch 4096 per GPU, AWGN Eb/N0 2 dB",
+                       "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}",
+                       "l2": "2 alternating input sets of 138 MB each (> 126 MB L2)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "ldpc_bp_kernel",
+                         "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_CW * BATCH},
+            "e2e": {"value": e2e_val, "unit": "coded bits/s", "h2d_bytes_per_step": BATCH * N_CODE * 4,
+                    "d2h_bytes_per_step": BATCH * K_INFO * 4, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "ber": {"bit_errors": c[0], "block_errors": c[1], "bits": c[2], "blocks": c[3]},
+        }
+        if not args.no_cpu_baseline:
+            from oracle import ldpc as O
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample or max(2 * cores, 64)
+            ref = O.LDPC5GDecoderRef(O.LDPC5GEncoderRef(K_INFO, N_CODE), cn_update=args.cn_update, num_iter=NUM_ITER)
+            x = h_in[0][:sample].numpy()
+            ref(x[:cores], num_threads=cores)
+            t0 = time.perf_counter()
+            u_ref = ref(x, num_threads=cores)
+            dt = time.perf_counter() - t0
+            u_gpu = dec(d_in[0][:sample]).cpu().numpy()
+            line["cpu_baseline"] = {"value": sample * N_CODE / dt, "unit": "coded bits/s", "cores": cores,
+                                    "kind": "port",
+                                    "sample": f"first {sample} codewords of the step-0 batch, oracle/ldpc_bp_ref.c libm "
+                                              f"mode, {cores} OpenMP threads",
+                                    "bit_mismatch_vs_gpu": int((u_ref != u_gpu).sum())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""ctypes binding of libsionna_b200.so (the C-ABI declared in include/sionna_b200.h).
+
+The library is built in-tree by ``sionna_b200.csrc.build`` (called from ``__graft_entry__.build()``).
+Loading fails loudly if it is missing: there is no Python / CPU fallback for any kernel.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsionna_b200.so")
+_lib = None
+
+i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+P_i32 = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); every symbol include/sionna_b200.h declares must be listed here
+# (tests/test_cabi.py checks header <-> table <-> library agree).
+SIGNATURES = {
+    "sb_last_error": (C.c_char_p, []),
+    "sb_device_info": (i32, [P_i32, P_i32, P_i32, P_i32]),
+    "sb_version": (i32, []),
+    "sb_ldpc_graph_create": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32]),
+    "sb_ldpc_graph_destroy": (None, [vp]),
+    "sb_ldpc_graph_on_chip": (i32, [vp]),
+    "sb_ldpc_workspace_bytes": (sz, [vp]),
+    "sb_ldpc_decode": (i32, [vp, vp, i64, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "sb_ldpc_last_launch_count": (i32, []),
+    "sb_ldpc_graph_export": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+}
+
+
+class SbError(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero status."""
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m sionna_b200.csrc.build` "
+                "(or __graft_entry__.build()). sionna_b200 has no fallback path without its CUDA library.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().sb_last_error().decode("utf-8", "replace")
+        raise SbError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array as c_void_p; None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,3 @@
+"""LDPC encoding / decoding (mirror of sionna.phy.fec.ldpc)."""
+from .encoding import LDPC5GEncoder
+from .decoding import LDPCBPDecoder, LDPC5GDecoder

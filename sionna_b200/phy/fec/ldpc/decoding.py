@@ -1,0 +1,373 @@
+"""LDPC belief-propagation decoders (mirror of /root/reference/src/sionna/phy/fec/ldpc/decoding.py).
+
+``LDPCBPDecoder`` (decoding.py:13-637) and ``LDPC5GDecoder`` (:1169-1536) keep the reference's constructor
+arguments, ``call(llr_ch, /, *, num_iter=None, msg_v2c=None)`` signature, logit sign convention and
+``msg_v2c`` state layout. All arithmetic runs in ``sb_ldpc_decode`` (``csrc/ldpc_bp.cu``): one CTA per
+codeword with the codeword's edge messages resident in shared memory for every iteration; rate recovery
+(:1431-1475) and output slicing / re-interleaving (:1486-1536) are folded into the kernel's load and store
+index maps, so the decoder moves 4*n bytes in and 4*k (or 4*n) bytes out per codeword and nothing else.
+"""
+import ctypes as C
+import types
+import numpy as np
+import scipy as sp
+import scipy.sparse  # noqa: F401
+import torch
+
+from ...block import Block
+from ...._lib import lib, check, ptr, current_stream
+from .encoding import LDPC5GEncoder
+
+_CN_RULES = {"boxplus-phi": 0, "boxplus": 1, "minsum": 2, "min": 2, "offset-minsum": 3, "identity": 4}
+_VN_RULES = {"sum": 0, "identity": 1}
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+
+
+class _GraphHandle:
+    """Owns one ``sb_ldpc_graph`` (host plan + lazily uploaded device tables)."""
+
+    def __init__(self, num_cn, num_vn, cn_idx, vn_idx, in_map=None, n_in=0, out_vn=None, n_out=0, schedule=None):
+        self._h = C.c_void_p()
+        cn_idx, vn_idx = _i32(cn_idx), _i32(vn_idx)
+        in_map = None if in_map is None else _i32(in_map)
+        out_vn = None if out_vn is None else _i32(out_vn)
+        n_sub = n_active = 0
+        if schedule is not None:
+            schedule = _i32(schedule)
+            n_sub, n_active = schedule.shape
+        check(lib().sb_ldpc_graph_create(C.byref(self._h), num_cn, num_vn, len(vn_idx), ptr(cn_idx), ptr(vn_idx),
+                                         ptr(in_map), int(n_in), ptr(out_vn), int(n_out), ptr(schedule),
+                                         int(n_sub), int(n_active)), "sb_ldpc_graph_create")
+        self.num_edges = len(vn_idx)
+        self.n_in = int(n_in) if in_map is not None else num_vn
+        self.n_out = int(n_out) if out_vn is not None else num_vn
+        self._ws = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def on_chip(self):
+        return bool(lib().sb_ldpc_graph_on_chip(self._h))
+
+    def workspace(self, device):
+        need = lib().sb_ldpc_workspace_bytes(self._h)
+        if need == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws, need
+
+    def export(self):
+        dims = np.zeros(10, np.int32)
+        check(lib().sb_ldpc_graph_export(self._h, ptr(dims), None, None, None, None, None, None), "export")
+        c, n, e, lc, lv = (int(x) for x in dims[:5])
+        out = {"dims": dims, "cn_order": np.zeros(c, np.int32), "vn_order": np.zeros(n, np.int32),
+               "slot_of_edge": np.zeros(e, np.int32), "vn_slot": np.zeros(e, np.int32),
+               "cn_off": np.zeros(lc + 1, np.int32), "vn_off": np.zeros(lv + 1, np.int32)}
+        check(lib().sb_ldpc_graph_export(self._h, ptr(dims), ptr(out["cn_order"]), ptr(out["vn_order"]),
+                                         ptr(out["slot_of_edge"]), ptr(out["vn_slot"]), ptr(out["cn_off"]),
+                                         ptr(out["vn_off"])), "export")
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().sb_ldpc_graph_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class LDPCBPDecoder(Block):
+    # pylint: disable=line-too-long
+    r"""LDPCBPDecoder(pcm, cn_update="boxplus-phi", vn_update="sum", cn_schedule="flooding", hard_out=True, num_iter=20, llr_max=20., v2c_callbacks=None, c2v_callbacks=None, return_state=False, precision=None)
+
+    Iterative belief-propagation decoder for arbitrary binary parity-check matrices
+    (reference: decoding.py:13-637). Inputs are logits ``log p(x=1)/p(x=0)`` of shape ``[..., n]``; the output is
+    the hard-decided codeword (``hard_out``) or soft logits, plus the ``[num_edges, batch]`` VN->CN message
+    state when ``return_state`` is set. ``cn_update`` is one of ``"boxplus-phi"`` (default), ``"boxplus"``,
+    ``"minsum"`` / ``"min"``, ``"offset-minsum"``, ``"identity"``; ``vn_update`` one of ``"sum"``, ``"identity"``.
+    """
+
+    def __init__(self, pcm, cn_update="boxplus-phi", vn_update="sum", cn_schedule="flooding", hard_out=True,
+                 num_iter=20, llr_max=20., v2c_callbacks=None, c2v_callbacks=None, return_state=False,
+                 precision=None, **kwargs):
+        if "cn_type" in kwargs:
+            raise TypeError("'cn_type' is deprecated; use 'cn_update' instead.")
+        super().__init__(precision=precision, **kwargs)
+        if not isinstance(hard_out, bool):
+            raise TypeError("hard_out must be bool.")
+        if not isinstance(num_iter, int):
+            raise TypeError("num_iter must be int.")
+        if num_iter < 0:
+            raise ValueError("num_iter cannot be negative.")
+        if not isinstance(return_state, bool):
+            raise TypeError("return_state must be bool.")
+        if isinstance(pcm, np.ndarray):
+            if not np.array_equal(pcm, pcm.astype(bool)):
+                raise ValueError("PC matrix must be binary.")
+        elif isinstance(pcm, (sp.sparse.csr_matrix, sp.sparse.csc_matrix)):
+            if not np.array_equal(pcm.data, pcm.data.astype(bool)):
+                raise ValueError("PC matrix must be binary.")
+        else:
+            raise TypeError("Unsupported dtype of pcm.")
+        if not isinstance(llr_max, (int, float)):
+            raise TypeError("llr_max must be int or float.")
+
+        self._pcm = pcm
+        self._hard_out = hard_out
+        self._num_iter = num_iter
+        self._return_state = return_state
+        self._num_cns, self._num_vns = pcm.shape[0], pcm.shape[1]
+        self._llr_max = float(llr_max)
+
+        for name, cbs in (("v2c_callbacks", v2c_callbacks), ("c2v_callbacks", c2v_callbacks)):
+            if cbs is None or (isinstance(cbs, (list, tuple)) and len(cbs) == 0):
+                continue
+            if isinstance(cbs, (list, tuple, types.FunctionType)):
+                raise NotImplementedError(
+                    f"{name}: per-iteration Python callbacks need the unfused message path, which this build "
+                    "does not provide; the fused sm_100a kernel keeps messages in shared memory.")
+            raise TypeError(f"{name} must be a list of callables.")
+        self._v2c_callbacks, self._c2v_callbacks = [], []
+
+        schedule = None
+        if isinstance(cn_schedule, str) and cn_schedule == "flooding":
+            self._scheduling = "flooding"
+            self._cn_schedule = np.arange(self._num_cns, dtype=np.int32)[None, :]
+        elif isinstance(cn_schedule, (np.ndarray, torch.Tensor)):
+            cs = np.asarray(cn_schedule.cpu() if isinstance(cn_schedule, torch.Tensor) else cn_schedule).astype(np.int32)
+            self._scheduling = "custom"
+            if cs.ndim != 2:
+                raise ValueError("cn_schedule must be of rank 2.")
+            if cs.max() >= self._num_cns:
+                raise ValueError("cn_schedule can only contain values smaller number_cns.")
+            if cs.min() < 0:
+                raise ValueError("cn_schedule cannot contain negative values.")
+            self._cn_schedule = cs
+            schedule = cs
+        else:
+            raise ValueError("cn_schedule can be 'flooding' or an array of ints.")
+
+        # edge list in the reference's VN order (decoding.py:277-292): same NumPy calls, same (unstable) argsort
+        if isinstance(pcm, np.ndarray):
+            pcm = sp.sparse.csr_matrix(pcm)
+        self._cn_idx, self._vn_idx, _ = sp.sparse.find(pcm)
+        idx = np.argsort(self._vn_idx)
+        self._cn_idx = self._cn_idx[idx]
+        self._vn_idx = self._vn_idx[idx]
+        self._num_edges = len(self._vn_idx)
+
+        if isinstance(cn_update, str) and cn_update in _CN_RULES:
+            self._cn_rule = _CN_RULES[cn_update]
+        elif isinstance(cn_update, types.FunctionType):
+            raise NotImplementedError("callable cn_update needs the unfused message path (not provided).")
+        else:
+            raise TypeError("Provided cn_update not supported.")
+        if isinstance(vn_update, str) and vn_update in _VN_RULES:
+            self._vn_rule = _VN_RULES[vn_update]
+        elif isinstance(vn_update, types.FunctionType):
+            raise NotImplementedError("callable vn_update needs the unfused message path (not provided).")
+        else:
+            raise TypeError("Provided vn_update not supported.")
+        self._offset = 0.5  # default of cn_update_offset_minsum (decoding.py:755)
+
+        in_map, n_in, out_vn, n_out = self._io_maps()
+        self._graph = _GraphHandle(self._num_cns, self._num_vns, self._cn_idx, self._vn_idx, in_map, n_in,
+                                   out_vn, n_out, schedule)
+
+    def _io_maps(self):
+        """Hook for subclasses folding rate matching into the kernel's load/store maps."""
+        return None, 0, None, 0
+
+    # ---- properties (decoding.py:351-410) -------------------------------------------------------------
+    @property
+    def pcm(self):
+        return self._pcm
+
+    @property
+    def num_cns(self):
+        return self._num_cns
+
+    @property
+    def num_vns(self):
+        return self._num_vns
+
+    @property
+    def n(self):
+        return self._num_vns
+
+    @property
+    def coderate(self):
+        return (self._num_vns - self._num_cns) / self._num_vns
+
+    @property
+    def num_edges(self):
+        return self._num_edges
+
+    @property
+    def num_iter(self):
+        return self._num_iter
+
+    @num_iter.setter
+    def num_iter(self, num_iter):
+        if not isinstance(num_iter, int):
+            raise TypeError("num_iter must be int.")
+        if num_iter < 0:
+            raise ValueError("num_iter cannot be negative.")
+        self._num_iter = num_iter
+
+    @property
+    def llr_max(self):
+        return self._llr_max
+
+    @llr_max.setter
+    def llr_max(self, value):
+        if value < 0:
+            raise ValueError("llr_max cannot be negative.")
+        self._llr_max = float(value)
+
+    @property
+    def return_state(self):
+        return self._return_state
+
+    @property
+    def on_chip(self):
+        """True if the decoding graph runs on the shared-memory-resident path."""
+        return self._graph.on_chip()
+
+    # ---- Block protocol -----------------------------------------------------------------------------
+    def build(self, input_shape, **kwargs):
+        assert input_shape[-1] == self._num_vns, "Last dimension must be of length n."
+
+    def _decode(self, llr2d, num_iter, msg_v2c):
+        if self.precision != "single":
+            raise NotImplementedError("sb_ldpc_decode is an fp32 kernel; precision='double' is not available.")
+        g = self._graph
+        dev = llr2d.device
+        b = llr2d.shape[0]
+        out = torch.empty((b, g.n_out), dtype=torch.float32, device=dev)
+        st_in = st_out = None
+        if msg_v2c is not None:
+            msg_v2c = torch.as_tensor(msg_v2c).to(device=dev, dtype=torch.float32)
+            if tuple(msg_v2c.shape) != (self._num_edges, b):
+                raise ValueError("msg_v2c must have shape [num_edges, batch_size].")
+            st_in = msg_v2c.t().contiguous()
+        if self._return_state:
+            st_out = torch.empty((b, self._num_edges), dtype=torch.float32, device=dev)
+        ws, ws_bytes = g.workspace(dev)
+        check(lib().sb_ldpc_decode(g.handle, ptr(llr2d), b, int(num_iter), self._cn_rule, self._vn_rule,
+                                   self._offset, self._llr_max, int(self._hard_out), ptr(st_in), ptr(st_out),
+                                   ptr(out), ptr(ws), ws_bytes, current_stream()), "sb_ldpc_decode")
+        return out, (st_out.t().contiguous() if st_out is not None else None)
+
+    def call(self, llr_ch, /, *, num_iter=None, msg_v2c=None):
+        if num_iter is None:
+            num_iter = self._num_iter
+        shape = list(llr_ch.shape)
+        llr2d = llr_ch.reshape(-1, self._num_vns).contiguous()
+        x, st = self._decode(llr2d, num_iter, msg_v2c)
+        x = x.reshape(shape[:-1] + [x.shape[-1]])
+        if not self._return_state:
+            return x
+        return x, st
+
+
+class LDPC5GDecoder(LDPCBPDecoder):
+    # pylint: disable=line-too-long
+    r"""LDPC5GDecoder(encoder, cn_update="boxplus-phi", vn_update="sum", cn_schedule="flooding", hard_out=True, return_infobits=True, num_iter=20, llr_max=20., v2c_callbacks=None, c2v_callbacks=None, prune_pcm=True, return_state=False, precision=None)
+
+    BP decoder for 5G NR LDPC codes including rate recovery (reference: decoding.py:1169-1536): takes ``[..., n]``
+    logits of the rate-matched codeword and returns the ``k`` information bits (``return_infobits``) or all ``n``
+    codeword positions. ``prune_pcm`` removes the trailing punctured degree-1 VNs and their CNs (:1344-1378);
+    ``cn_schedule="layered"`` updates groups of Z check nodes sequentially (:1384-1390).
+    """
+
+    def __init__(self, encoder, cn_update="boxplus-phi", vn_update="sum", cn_schedule="flooding", hard_out=True,
+                 return_infobits=True, num_iter=20, llr_max=20., v2c_callbacks=None, c2v_callbacks=None,
+                 prune_pcm=True, return_state=False, precision=None, **kwargs):
+        if not isinstance(encoder, LDPC5GEncoder):
+            raise TypeError("encoder must be of class LDPC5GEncoder.")
+        self._encoder = encoder
+        pcm = encoder.pcm
+        if not isinstance(return_infobits, bool):
+            raise TypeError("return_info must be bool.")
+        self._return_infobits = return_infobits
+        if not isinstance(return_state, bool):
+            raise TypeError("return_state must be bool.")
+        if "cn_type" in kwargs:
+            raise TypeError("'cn_type' is deprecated; use 'cn_update' instead.")
+        if not isinstance(prune_pcm, bool):
+            raise TypeError("prune_pcm must be bool.")
+        self._prune_pcm = prune_pcm
+        k_filler = encoder.k_ldpc - encoder.k
+        nb_punc_bits = (encoder.n_ldpc - k_filler) - encoder.n - 2 * encoder.z
+        if prune_pcm:
+            # first index of the trailing run of degree-1 columns (decoding.py:1346-1352)
+            dv = np.asarray(pcm.sum(axis=0)).ravel()
+            last_pos = encoder.n_ldpc
+            for idx in range(encoder.n_ldpc - 1, 0, -1):
+                if dv[idx] == 1:
+                    last_pos = idx
+                else:
+                    break
+            if isinstance(cn_schedule, str) and cn_schedule == "layered":
+                nb_punc_bits = int(np.floor(nb_punc_bits / encoder.z) * encoder.z)
+            self._n_pruned = int(max(last_pos, encoder.n_ldpc - nb_punc_bits))
+            self._nb_pruned_nodes = encoder.n_ldpc - self._n_pruned
+            if self._nb_pruned_nodes < 0:
+                raise ArithmeticError("Internal error: number of pruned nodes must be positive.")
+            if self._nb_pruned_nodes > 0:
+                pcm = pcm[:-self._nb_pruned_nodes, :-self._nb_pruned_nodes]
+        else:
+            self._nb_pruned_nodes = 0
+            self._n_pruned = encoder.n_ldpc
+        if isinstance(cn_schedule, str) and cn_schedule == "layered":
+            z = encoder.z
+            num_blocks = int(pcm.shape[0] / z)
+            cn_schedule = np.stack([np.arange(z) + i * z for i in range(num_blocks)], axis=0)
+        super().__init__(sp.sparse.csr_matrix(pcm), cn_update=cn_update, vn_update=vn_update,
+                         cn_schedule=cn_schedule, hard_out=hard_out, num_iter=num_iter, llr_max=llr_max,
+                         v2c_callbacks=v2c_callbacks, c2v_callbacks=c2v_callbacks, return_state=return_state,
+                         precision=precision, **kwargs)
+
+    @property
+    def encoder(self):
+        return self._encoder
+
+    def _io_maps(self):
+        """Fold decoding.py:1436-1475 (input) and :1486-1536 (output) into gather maps over the pruned VNs."""
+        enc = self._encoder
+        k, k_ldpc, z, n = enc.k, enc.k_ldpc, enc.z, enc.n
+        k_filler = k_ldpc - k
+        v = np.arange(self._n_pruned)
+        q = np.where(v < k, v, v - k_filler)                  # position in [0(2Z) | llr(n) | 0(punct)]
+        i = q - 2 * z                                         # position in the (de-interleaved) received word
+        src = i if enc.out_int_inv is None else np.asarray(enc.out_int_inv)[np.clip(i, 0, n - 1)]
+        in_map = np.where((i >= 0) & (i < n), src, -1)
+        in_map = np.where((v >= k) & (v < k_ldpc), -2, in_map).astype(np.int32)
+        if self._return_infobits:
+            out_vn = np.arange(k, dtype=np.int32)
+        else:
+            out_vn = enc._tx_vn()
+        return in_map, n, out_vn, len(out_vn)
+
+    def build(self, input_shape, **kwargs):
+        if input_shape[-1] != self.encoder.n:
+            raise ValueError("Last dimension must be of length n.")
+        self._old_shape_5g = input_shape
+
+    def call(self, llr_ch, /, *, num_iter=None, msg_v2c=None):
+        if num_iter is None:
+            num_iter = self._num_iter
+        shape = list(llr_ch.shape)
+        llr2d = llr_ch.reshape(-1, self.encoder.n).contiguous()
+        x, st = self._decode(llr2d, num_iter, msg_v2c)
+        x = x.reshape(shape[:-1] + [x.shape[-1]])
+        if self._return_state:
+            return x, st
+        return x

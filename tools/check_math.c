@@ -1,0 +1,44 @@
+// Exhaustive accuracy check of sb_math.h against float64 libm.  gcc -O2 -ffp-contract=off -mfma -fopenmp
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include <float.h>
+#include "../sionna_b200/csrc/sb_math.h"
+static double ulp_of(double ref) { float f = (float)ref; if (f == 0) return FLT_MIN; int e; frexpf(fabsf(f), &e); return ldexp(1.0, e - 24); }
+int main(void) {
+    double worst_exp = 0, worst_log = 0, worst_tanh = 0, worst_atanh = 0; float wx = 0, wl = 0, wt = 0, wa = 0;
+    #pragma omp parallel
+    {
+        double we = 0, wlg = 0, wth = 0, wat = 0; float xe = 0, xl = 0, xt = 0, xa = 0;
+        #pragma omp for schedule(static)
+        for (long long i = 0; i < (1LL << 32); ++i) {
+            uint32_t u = (uint32_t)i; float x; memcpy(&x, &u, 4);
+            if (!(x == x) || isinf(x)) continue;
+            if (x >= -87.3f && x <= 88.7f) {
+                double ref = exp((double)x); double err = fabs((double)sb_expf(x) - ref) / ulp_of(ref);
+                if (err > we) { we = err; xe = x; }
+            }
+            if (x >= FLT_MIN) {
+                double ref = log((double)x); double err = fabs((double)sb_logf(x) - ref) / ulp_of(ref);
+                if (err > wlg) { wlg = err; xl = x; }
+            }
+            if (fabsf(x) <= 20.f && fabsf(x) >= 1e-30f) {
+                double ref = tanh((double)x); double err = fabs((double)sb_tanhf(x) - ref) / ulp_of(ref);
+                if (err > wth) { wth = err; xt = x; }
+            }
+            if (fabsf(x) < 1.0f && fabsf(x) >= 1e-30f) {
+                double ref = atanh((double)x); double err = fabs((double)sb_atanhf(x) - ref) / ulp_of(ref);
+                if (err > wat) { wat = err; xa = x; }
+            }
+        }
+        #pragma omp critical
+        { if (we > worst_exp) { worst_exp = we; wx = xe; } if (wlg > worst_log) { worst_log = wlg; wl = xl; }
+          if (wth > worst_tanh) { worst_tanh = wth; wt = xt; } if (wat > worst_atanh) { worst_atanh = wat; wa = xa; } }
+    }
+    printf("expf max ulp err %.4f at %a\nlogf max ulp err %.4f at %a\ntanhf max ulp err %.4f at %a\natanhf max ulp err %.4f at %a\n",
+           worst_exp, wx, worst_log, wl, worst_tanh, wt, worst_atanh, wa);
+    float x = 8.5e-8f; printf("exp(8.5e-8)=%a  phi(0)=%.9g phi(8.5e-8)=%.9g phi(1)=%.9g phi(10)=%.9g phi(16)=%.9g phi(16.635532)=%.9g phi(40)=%.9g\n",
+        sb_expf(x), sb_phif(0.f), sb_phif(x), sb_phif(1.f), sb_phif(10.f), sb_phif(16.f), sb_phif(16.635532f), sb_phif(40.f));
+    printf("log(2^24)=%a log(2^24-1)=%a phi(2*phi(0))=%g\n", sb_logf(16777216.f), sb_logf(16777215.f), sb_phif(2*sb_phif(0.f)));
+    return 0;
+}
