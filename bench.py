@@ -183,17 +183,17 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
+    launches0 = _lib.lib().sb_launch_count()
     t_start.record()
     for i in range(args.steps):
         ev[i][0].record()
         u_hat = dec(d_in[i & 1])
         ev[i][1].record()
-        launches += _lib.lib().sb_ldpc_last_launch_count()
         count(u_hat)
         if world > 1:
             dist.all_reduce(counters_step.copy_(counters), op=dist.ReduceOp.SUM)
     t_stop.record()
+    launches = _lib.lib().sb_launch_count() - launches0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -38,6 +38,9 @@ const char* sb_last_error(void);
  * opt-in shared memory per block of the CURRENT device. */
 int sb_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes);
 int sb_version(void);
+/* Number of kernels this library has launched from the calling thread since it was loaded (bench.py reports the
+ * difference over its timed region as gpu_launches). */
+int64_t sb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * LDPC belief propagation
@@ -90,8 +93,51 @@ int sb_ldpc_decode(const sb_ldpc_graph* g, const float* d_llr, int64_t batch, in
                    int32_t cn_rule, int32_t vn_rule, float offset, float llr_max, int32_t hard_out,
                    const float* d_state_in, float* d_state_out, float* d_out,
                    void* d_workspace, size_t workspace_bytes, void* stream);
-/* Number of kernels the last sb_ldpc_decode on this thread launched (for bench.py's gpu_launches). */
-int sb_ldpc_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 5G NR LDPC encoder with rate matching
+ * replaces LDPC5GEncoder.call / _encode_fast / _matmul_gather   fec/ldpc/encoding.py:599-668, 572-591, 559-570
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sb_ldpc5g_encoder sb_ldpc5g_encoder;
+/* CSR (row pointer, ascending column index) of the binary Richardson-Urbanke sub-matrices of the lifted
+ * parity-check matrix H = [[A B 0],[C1 C2 I]] (encoding.py:411-434): A [g_rows x k_ldpc], B^-1 [g_rows x g_rows],
+ * C1 [(n_ldpc-k_ldpc-g_rows) x k_ldpc], C2 [same rows x g_rows]; h_tx_vn[n]: index into the n_ldpc-bit codeword
+ * [s | p_a | p_b] transmitted at output position j (filler removal, 2Z puncturing, truncation, interleaver of
+ * encoding.py:645-661 folded into one gather). */
+int sb_ldpc5g_encoder_create(sb_ldpc5g_encoder** out, int32_t k, int32_t n, int32_t k_ldpc, int32_t n_ldpc,
+                             int32_t g_rows, const int32_t* h_a_ptr, const int32_t* h_a_idx,
+                             const int32_t* h_binv_ptr, const int32_t* h_binv_idx, const int32_t* h_c1_ptr,
+                             const int32_t* h_c1_idx, const int32_t* h_c2_ptr, const int32_t* h_c2_idx,
+                             const int32_t* h_tx_vn);
+void sb_ldpc5g_encoder_destroy(sb_ldpc5g_encoder* e);
+/* d_u [batch, k] information bits as 0.0f/1.0f -> d_c [batch, n] codeword bits as 0.0f/1.0f. */
+int sb_ldpc5g_encode(const sb_ldpc5g_encoder* e, const float* d_u, int64_t batch, float* d_c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sources, mapping, channel noise, metrics
+ * ---------------------------------------------------------------------------------------------- */
+/* BinarySource.call (mapping.py:1350-1352): n i.i.d. uniform bits as 0.0f/1.0f from Philox4x32-10(seed, offset). */
+int sb_binary_source(float* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* out = mean + stddev * N(0,1) (GaussianPriorSource, fec/utils.py:71-114). */
+int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint64_t seed, uint64_t offset, void* stream);
+/* Mapper.call (mapping.py:497-519): d_bits [n_sym, m] 0/1 floats, MSB first -> d_out [n_sym] complex64 =
+ * d_points[index]; d_idx_out (optional, int32 [n_sym]) receives the symbol indices (return_indices). */
+int sb_qam_map(const float* d_bits, const float* d_points, int32_t m, float* d_out, int32_t* d_idx_out,
+               int64_t n_sym, void* stream);
+/* Demapper.call + SymbolLogits2LLRs.call (mapping.py:664-691, 927-967).
+ *   d_y [n_sym] complex64; d_no: noise variance, element s uses d_no[s / no_inner] (no_inner = n_sym for a scalar,
+ *   1 for per-symbol); d_points [2^m] complex64; method 0 = "app", 1 = "maxlog";
+ *   d_prior (optional): prior logits, symbol s uses d_prior[(s / prior_inner) * m .. +m);
+ *   d_llr [n_sym * m] logits log p(1)/p(0), or hard decisions (llr > 0) when hard_out != 0. */
+int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, const float* d_points, int32_t m, int32_t method,
+             const float* d_prior, int64_t prior_inner, float* d_llr, int64_t n_sym, int32_t hard_out, void* stream);
+/* AWGN.call (channel/awgn.py:63-78, utils/misc.py:19-54): y = x + sqrt(no) * CN(0,1), complex64 [n];
+ * element i uses d_no[i / no_inner]. */
+int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, int64_t n, uint64_t seed,
+            uint64_t offset, void* stream);
+/* count_errors / count_block_errors (utils/metrics.py:94-144) fused: for b, b_hat [rows, k] (0/1 floats)
+ * d_counters[0] += #(b != b_hat); [1] += #rows with any difference; [2] += rows*k; [3] += rows  (int64[4], device). */
+int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_t k, int64_t* d_counters, void* stream);
 
 #ifdef __cplusplus
 }

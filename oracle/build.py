@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_build", "libsbo.so")
-SRCS = ["ldpc_bp_ref.c"]
+SRCS = ["ldpc_bp_ref.c", "mapping_ref.c"]
 
 
 def build(force=False):

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsionna_b200.so")
 _lib = None
 
-i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+i32, i64, u64, f32, vp, sz = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
 P_i32 = C.POINTER(C.c_int32)
 
 # name -> (restype, argtypes); every symbol include/sionna_b200.h declares must be listed here
@@ -19,13 +19,22 @@ SIGNATURES = {
     "sb_last_error": (C.c_char_p, []),
     "sb_device_info": (i32, [P_i32, P_i32, P_i32, P_i32]),
     "sb_version": (i32, []),
+    "sb_launch_count": (i64, []),
     "sb_ldpc_graph_create": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32]),
     "sb_ldpc_graph_destroy": (None, [vp]),
     "sb_ldpc_graph_on_chip": (i32, [vp]),
     "sb_ldpc_workspace_bytes": (sz, [vp]),
     "sb_ldpc_decode": (i32, [vp, vp, i64, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]),
-    "sb_ldpc_last_launch_count": (i32, []),
     "sb_ldpc_graph_export": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "sb_ldpc5g_encoder_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32] + [vp] * 9),
+    "sb_ldpc5g_encoder_destroy": (None, [vp]),
+    "sb_ldpc5g_encode": (i32, [vp, vp, i64, vp, vp]),
+    "sb_binary_source": (i32, [vp, i64, u64, u64, vp]),
+    "sb_normal": (i32, [vp, i64, f32, f32, u64, u64, vp]),
+    "sb_qam_map": (i32, [vp, vp, i32, vp, vp, i64, vp]),
+    "sb_demap": (i32, [vp, vp, i64, vp, i32, i32, vp, i64, vp, i64, i32, vp]),
+    "sb_awgn": (i32, [vp, vp, i64, vp, i64, u64, u64, vp]),
+    "sb_count_errors": (i32, [vp, vp, i64, i32, vp, vp]),
 }
 
 

@@ -3,7 +3,7 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
-static thread_local int g_launches = 0;
+static thread_local long long g_launches = 0;
 
 void sb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -12,11 +12,10 @@ void sb_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void sb_count_launch(void) { ++g_launches; }
-void sb_reset_launch_count(void) { g_launches = 0; }
 
 extern "C" const char* sb_last_error(void) { return g_err; }
 extern "C" int sb_version(void) { return 100; }
-extern "C" int sb_ldpc_last_launch_count(void) { return g_launches; }
+extern "C" int64_t sb_launch_count(void) { return g_launches; }
 
 extern "C" int sb_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
     int dev = 0;

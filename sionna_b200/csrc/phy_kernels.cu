@@ -1,0 +1,275 @@
+// phy_kernels.cu -- bytes-bound element-wise kernels of the link-level chain (sm_100a):
+//   sb_binary_source   BinarySource.call                 mapping.py:1350-1352
+//   sb_qam_map         Mapper.call                       mapping.py:497-519
+//   sb_demap           Demapper.call + SymbolLogits2LLRs mapping.py:664-691, 927-967
+//   sb_awgn            AWGN.call + complex_normal        channel/awgn.py:63-78, utils/misc.py:19-54
+//   sb_count_errors    count_errors / count_block_errors utils/metrics.py:94-144
+// (paths relative to /root/reference/src/sionna/phy). All are one pass over HBM with coalesced accesses and
+// grids sized as a multiple of the SM count; transcendental functions of the demapper come from sb_math.h so the
+// CPU oracle reproduces LLRs bit for bit.
+#include "sb_common.h"
+#include "sb_math.h"
+#include "rng.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void binary_source_kernel(float* __restrict__ out, long long n, unsigned long long seed,
+                                     unsigned long long offset) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one Philox block -> 128 bits
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long blk = i; blk * 128 < n; blk += stride) {
+        uint4 r = philox4x32_10(seed, offset, (unsigned long long)blk);
+        unsigned w[4] = {r.x, r.y, r.z, r.w};
+        long long base = blk * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                long long idx = base + k * 32 + b;
+                if (idx < n) out[idx] = (float)((w[k] >> b) & 1u);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bits [n_sym, m] (float 0/1) -> points[index], index = sum bit_k << (m-1-k)   (mapping.py:500-514)
+__global__ void qam_map_kernel(const float* __restrict__ bits, const float2* __restrict__ points, int m,
+                               float2* __restrict__ out, int* __restrict__ idx_out, long long n_sym) {
+    extern __shared__ float2 s_pts[];
+    for (int i = threadIdx.x; i < (1 << m); i += blockDim.x) s_pts[i] = points[i];
+    __syncthreads();
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_sym; s += stride) {
+        int v = 0;
+        for (int k = 0; k < m; ++k) v = (v << 1) | ((int)bits[s * m + k] & 1);
+        out[s] = s_pts[v];
+        if (idx_out) idx_out[s] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// log_sigmoid(x) = -softplus(-x) with TensorFlow's softplus branches (threshold = log(eps) + 2)
+__device__ __forceinline__ float log1p_pos(float u) {   // u >= 0
+    float w = __fadd_rn(1.f, u);
+    if (w == 1.f) return u;
+    return __fmul_rn(sb_logf(w), __fdiv_rn(u, __fsub_rn(w, 1.f)));
+}
+__device__ __forceinline__ float softplusf(float x) {
+    const float threshold = -13.942385f;   // logf(FLT_EPSILON) + 2
+    if (x > -threshold) return x;
+    float ex = sb_expf(x);
+    if (x < threshold) return ex;
+    return log1p_pos(ex);
+}
+__device__ __forceinline__ float log_sigmoidf(float x) { return -softplusf(-x); }
+
+// One thread per symbol. exponents e_j = -|y - c_j|^2 / max(no, tiny) (+ prior term), then for every bit i:
+// app: logsumexp over points with bit i = 1 minus the same over bit i = 0; maxlog: max instead.
+template <int METHOD>   // 0 = app, 1 = maxlog
+__global__ void demap_kernel(const float2* __restrict__ y, const float* __restrict__ no, long long no_inner,
+                             const float2* __restrict__ points, int m, const float* __restrict__ prior,
+                             long long prior_inner, float* __restrict__ llr, long long n_sym, int hard_out) {
+    extern __shared__ float2 s_pts[];
+    const int npts = 1 << m;
+    for (int i = threadIdx.x; i < npts; i += blockDim.x) s_pts[i] = points[i];
+    __syncthreads();
+    const float tiny = 1.17549435e-38f;   // np.finfo(float32).tiny (mapping.py:653)
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_sym; s += stride) {
+        float2 yy = y[s];
+        float n0 = fmaxf(no[s / no_inner], tiny);
+        const float* pr = prior ? prior + (s / prior_inner) * m : nullptr;
+        for (int i = 0; i < m; ++i) {
+            const int bitmask = 1 << (m - 1 - i);          // label bit i, MSB first (mapping.py:894-907)
+            float acc[2];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                float mx = -INFINITY;
+                // pass 1: maximum of the exponents over the subset
+                for (int j = 0; j < npts; ++j) {
+                    if (((j & bitmask) != 0) != (v == 1)) continue;
+                    float dr = __fsub_rn(yy.x, s_pts[j].x), di = __fsub_rn(yy.y, s_pts[j].y);
+                    float a = __fsqrt_rn(__fmaf_rn(dr, dr, __fmul_rn(di, di)));     // |y - c|  (tf.abs)
+                    float e = __fdiv_rn(-__fmul_rn(a, a), n0);                       // -|.|^2 / no
+                    if (pr) {
+                        float ps = 0.f;
+                        for (int k = 0; k < m; ++k) {
+                            float lab = ((j >> (m - 1 - k)) & 1) ? 1.f : -1.f;
+                            ps = __fadd_rn(ps, log_sigmoidf(__fmul_rn(lab, pr[k])));
+                        }
+                        e = __fadd_rn(ps, e);
+                    }
+                    mx = fmaxf(mx, e);
+                }
+                if (METHOD == 1) { acc[v] = mx; continue; }
+                // tf.reduce_logsumexp: log(sum(exp(x - max))) + max, max replaced by 0 if not finite
+                float mm = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
+                float sum = 0.f;
+                for (int j = 0; j < npts; ++j) {
+                    if (((j & bitmask) != 0) != (v == 1)) continue;
+                    float dr = __fsub_rn(yy.x, s_pts[j].x), di = __fsub_rn(yy.y, s_pts[j].y);
+                    float a = __fsqrt_rn(__fmaf_rn(dr, dr, __fmul_rn(di, di)));
+                    float e = __fdiv_rn(-__fmul_rn(a, a), n0);
+                    if (pr) {
+                        float ps = 0.f;
+                        for (int k = 0; k < m; ++k) {
+                            float lab = ((j >> (m - 1 - k)) & 1) ? 1.f : -1.f;
+                            ps = __fadd_rn(ps, log_sigmoidf(__fmul_rn(lab, pr[k])));
+                        }
+                        e = __fadd_rn(ps, e);
+                    }
+                    sum = __fadd_rn(sum, sb_expf(__fsub_rn(e, mm)));
+                }
+                acc[v] = __fadd_rn(sum > 0.f ? sb_logf(sum) : -INFINITY, mm);
+            }
+            float l = __fsub_rn(acc[1], acc[0]);
+            llr[s * m + i] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;     // hard_decisions: utils/misc.py:270
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// y = x + sqrt(no) * n,  n ~ CN(0, 1): re, im ~ N(0, 1/2) (utils/misc.py:46-52, channel/awgn.py:66-78).
+// One Philox block (4 uniforms -> 2 Box-Muller pairs) serves two complex samples.
+__global__ void awgn_kernel(const float2* x, const float* __restrict__ no, long long no_inner,
+                            float2* y, long long n, unsigned long long seed, unsigned long long offset) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    const float stddev = 0.70710678118654752f;   // sqrt(var/2), var = 1
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; 2 * p < n; p += stride) {
+        uint4 r = philox4x32_10(seed, offset, (unsigned long long)p);
+        float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+        long long i0 = 2 * p, i1 = 2 * p + 1;
+        float s0 = sqrtf(no[i0 / no_inner]);
+        float2 a = x[i0];
+        y[i0] = make_float2(a.x + (g0.x * stddev) * s0, a.y + (g0.y * stddev) * s0);
+        if (i1 < n) {
+            float s1 = sqrtf(no[i1 / no_inner]);
+            float2 b = x[i1];
+            y[i1] = make_float2(b.x + (g1.x * stddev) * s1, b.y + (g1.y * stddev) * s1);
+        }
+    }
+}
+
+// real-valued variant used for LLR-domain test sources (GaussianPriorSource): out = mean + std * N(0,1)
+__global__ void normal_kernel(float* __restrict__ out, long long n, float mean, float stdv, unsigned long long seed,
+                              unsigned long long offset) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; 4 * p < n; p += stride) {
+        uint4 r = philox4x32_10(seed, offset, (unsigned long long)p);
+        float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+        float v[4] = {g0.x, g0.y, g1.x, g1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * p + k < n) out[4 * p + k] = mean + stdv * v[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// counters[0] += #(b != b_hat), counters[1] += #rows with any difference, counters[2] += B*k, counters[3] += B.
+// One warp per row; block-level reduction, one atomic per block and counter.
+__global__ void count_errors_kernel(const float* __restrict__ b, const float* __restrict__ bh, long long rows, int k,
+                                    unsigned long long* __restrict__ counters) {
+    __shared__ unsigned long long s_bit[32], s_blk[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long bit_e = 0, blk_e = 0;
+    for (long long r = (long long)blockIdx.x * nwarps + warp; r < rows; r += (long long)gridDim.x * nwarps) {
+        const float* pb = b + r * k;
+        const float* ph = bh + r * k;
+        unsigned cnt = 0;
+        for (int i = lane; i < k; i += 32) cnt += (pb[i] != ph[i]);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        bit_e += cnt;
+        blk_e += (cnt != 0);
+    }
+    if (lane == 0) { s_bit[warp] = bit_e; s_blk[warp] = blk_e; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tb = 0, tk = 0;
+        for (int w = 0; w < nwarps; ++w) { tb += s_bit[w]; tk += s_blk[w]; }
+        if (tb) atomicAdd(&counters[0], tb);
+        if (tk) atomicAdd(&counters[1], tk);
+        if (blockIdx.x == 0) {
+            atomicAdd(&counters[2], (unsigned long long)rows * (unsigned long long)k);
+            atomicAdd(&counters[3], (unsigned long long)rows);
+        }
+    }
+}
+
+inline int grid_for(long long work_items, int threads) {
+    int sms = sb_num_sms();
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;                       // grid-stride beyond 8 CTAs per SM
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int sb_binary_source(float* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    SB_CHECK_ARG(d_out && n >= 0, "sb_binary_source: bad arguments");
+    if (n == 0) return SB_OK;
+    binary_source_kernel<<<grid_for((n + 127) / 128, 128), 128, 0, (cudaStream_t)stream>>>(d_out, n, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_qam_map(const float* d_bits, const float* d_points, int32_t m, float* d_out, int32_t* d_idx_out,
+                          int64_t n_sym, void* stream) {
+    SB_CHECK_ARG(d_bits && d_points && d_out && m >= 1 && m <= 12 && n_sym >= 0, "sb_qam_map: bad arguments");
+    if (n_sym == 0) return SB_OK;
+    size_t smem = sizeof(float2) << m;
+    qam_map_kernel<<<grid_for(n_sym, 256), 256, smem, (cudaStream_t)stream>>>(
+        d_bits, (const float2*)d_points, m, (float2*)d_out, d_idx_out, n_sym);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, const float* d_points, int32_t m,
+                        int32_t method, const float* d_prior, int64_t prior_inner, float* d_llr, int64_t n_sym,
+                        int32_t hard_out, void* stream) {
+    SB_CHECK_ARG(d_y && d_no && d_points && d_llr && m >= 1 && m <= 12 && n_sym >= 0 && no_inner >= 1,
+                 "sb_demap: bad arguments");
+    SB_CHECK_ARG(method == 0 || method == 1, "sb_demap: method must be 0 (app) or 1 (maxlog)");
+    SB_CHECK_ARG(!d_prior || prior_inner >= 1, "sb_demap: prior_inner must be >= 1");
+    if (n_sym == 0) return SB_OK;
+    size_t smem = sizeof(float2) << m;
+    int grid = grid_for(n_sym, 128);
+    if (method == 0)
+        demap_kernel<0><<<grid, 128, smem, (cudaStream_t)stream>>>((const float2*)d_y, d_no, no_inner, (const float2*)d_points,
+                                                                  m, d_prior, prior_inner, d_llr, n_sym, hard_out);
+    else
+        demap_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>((const float2*)d_y, d_no, no_inner, (const float2*)d_points,
+                                                                  m, d_prior, prior_inner, d_llr, n_sym, hard_out);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, int64_t n, uint64_t seed,
+                       uint64_t offset, void* stream) {
+    SB_CHECK_ARG(d_x && d_no && d_y && n >= 0 && no_inner >= 1, "sb_awgn: bad arguments");
+    if (n == 0) return SB_OK;
+    awgn_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)d_x, d_no, no_inner,
+                                                                              (float2*)d_y, n, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint64_t seed, uint64_t offset, void* stream) {
+    SB_CHECK_ARG(d_out && n >= 0, "sb_normal: bad arguments");
+    if (n == 0) return SB_OK;
+    normal_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(d_out, n, mean, stddev, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_t k, int64_t* d_counters,
+                               void* stream) {
+    SB_CHECK_ARG(d_b && d_b_hat && d_counters && rows >= 0 && k >= 1, "sb_count_errors: bad arguments");
+    if (rows == 0) return SB_OK;
+    count_errors_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_b, d_b_hat, rows, k, (unsigned long long*)d_counters);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}

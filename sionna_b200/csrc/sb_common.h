@@ -8,7 +8,6 @@
 // thread-local error message (defined in common.cu)
 void sb_set_error(const char* fmt, ...);
 void sb_count_launch(void);
-void sb_reset_launch_count(void);
 
 #define SB_CHECK_ARG(cond, ...)                  \
     do {                                         \

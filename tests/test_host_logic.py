@@ -1,0 +1,144 @@
+"""Host-side logic that needs no GPU: code construction, decoder graph plan (jagged-diagonal slot layout built in
+C++), rate-recovery maps vs the oracle's literal concat/slice restatement, API argument checks."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import ldpc as O
+
+
+@pytest.mark.parametrize("k,n", [(12, 20), (64, 128), (292, 500), (300, 500), (3824, 5800), (3825, 5800), (640, 3000),
+                                 (4224, 8448), (8448, 9000), (8448, 25344)])
+def test_code_construction_matches_oracle(k, n):
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder
+    enc, ref = LDPC5GEncoder(k, n), O.LDPC5GEncoderRef(k, n)
+    assert (enc._bg, enc.z, enc._i_ls, enc.k_ldpc, enc.n_ldpc) == (ref.bg, ref.z, ref.i_ls, ref.k_ldpc, ref.n_ldpc)
+    assert (enc.pcm != ref.pcm).nnz == 0
+    # closed-form B^-1 (product) really inverts B over GF(2)
+    _, b_inv, _, _ = enc._ru_submatrices()
+    prod = (b_inv @ ref.Bm).toarray() % 2
+    assert np.array_equal(prod, np.eye(4 * enc.z))
+
+
+def test_benchmark_graph_dimensions():
+    """C=4608, N=8832, E=40320 and the degree histograms of the n=8448 decoding graph."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    dec = LDPC5GDecoder(LDPC5GEncoder(4224, 8448))
+    assert (dec.num_cns, dec.num_vns, dec.num_edges) == (4608, 8832, 40320)
+    cd, vd = np.bincount(dec._cn_idx), np.bincount(dec._vn_idx)
+    assert dict(zip(*np.unique(cd, return_counts=True))) == {3: 192, 5: 384, 6: 1344, 7: 960, 8: 384, 9: 384, 10: 192, 19: 768}
+    assert dict(zip(*np.unique(vd, return_counts=True))) == {1: 3840, 3: 384, 4: 960, 5: 576, 6: 384, 7: 192, 8: 960,
+                                                            9: 1152, 17: 192, 19: 192}
+    assert dec.on_chip
+
+
+def _check_plan(dec):
+    ex = dec._graph.export()
+    C_, N_, E_, Lc, Lv = (int(x) for x in ex["dims"][:5])
+    cn_idx, vn_idx = np.asarray(dec._cn_idx), np.asarray(dec._vn_idx)
+    cdeg, vdeg = np.bincount(cn_idx, minlength=C_), np.bincount(vn_idx, minlength=N_)
+    # ranks: degree descending, stable
+    assert np.array_equal(ex["cn_order"], np.argsort(-cdeg, kind="stable"))
+    assert np.array_equal(ex["vn_order"], np.argsort(-vdeg, kind="stable"))
+    crank = np.empty(C_, int); crank[ex["cn_order"]] = np.arange(C_)
+    vrank = np.empty(N_, int); vrank[ex["vn_order"]] = np.arange(N_)
+    slot = ex["slot_of_edge"]
+    assert sorted(slot) == list(range(E_))                       # a permutation of the slots
+    for c in np.random.default_rng(0).choice(C_, min(C_, 50), replace=False):
+        es = np.nonzero(cn_idx == c)[0]
+        es = es[np.argsort(vn_idx[es])]                          # ascending VN
+        assert [slot[e] for e in es] == [ex["cn_off"][l] + crank[c] for l in range(len(es))]
+    for v in np.random.default_rng(1).choice(N_, min(N_, 50), replace=False):
+        es = np.nonzero(vn_idx == v)[0]
+        es = es[np.argsort(cn_idx[es])]                          # ascending CN
+        assert [ex["vn_slot"][ex["vn_off"][l] + vrank[v]] for l in range(len(es))] == [slot[e] for e in es]
+
+
+def test_graph_plan_jds_layout():
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder, LDPCBPDecoder
+    from sionna_b200.phy.fec.utils import load_parity_check_examples
+    _check_plan(LDPC5GDecoder(LDPC5GEncoder(200, 500)))
+    for i in range(5):
+        _check_plan(LDPCBPDecoder(load_parity_check_examples(i)[0]))
+
+
+@pytest.mark.parametrize("k,n,m,prune,info", [(100, 200, None, True, True), (100, 200, None, False, False),
+                                               (300, 720, 6, True, False), (64, 180, 4, False, True),
+                                               (4224, 8448, 2, True, False)])
+def test_rate_recovery_maps_equal_reference_concat_slices(k, n, m, prune, info):
+    """The kernel's load/store gather maps reproduce LDPC5GDecoder.call's concat/slice sequence
+    (decoding.py:1431-1536), checked with a 0-iteration oracle decode on a ramp input."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    enc = LDPC5GEncoder(k, n, num_bits_per_symbol=m)
+    dec = LDPC5GDecoder(enc, prune_pcm=prune, return_infobits=info, hard_out=False)
+    in_map, n_in, out_vn, n_out = dec._io_maps()
+    enc_r = O.LDPC5GEncoderRef(k, n, num_bits_per_symbol=m)
+    ref = O.LDPC5GDecoderRef(enc_r, prune_pcm=prune, return_infobits=info, hard_out=False, num_iter=0, llr_max=1e9)
+    assert ref.n_pruned == dec._n_pruned and (ref.pcm != dec.pcm).nnz == 0
+    x = (np.arange(n, dtype=np.float32) + 1.0)[None, :]
+    vn_vals = np.where(in_map >= 0, x[0, np.clip(in_map, 0, n - 1)], np.where(in_map == -1, 0.0, -1e9))
+    assert np.array_equal(vn_vals[out_vn][None, :], ref(x))
+    assert n_in == n and n_out == (k if info else n)
+
+
+def test_layered_schedule_and_pruning_quantisation():
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    enc = LDPC5GEncoder(200, 450)
+    dec = LDPC5GDecoder(enc, cn_schedule="layered")
+    ref = O.LDPC5GDecoderRef(O.LDPC5GEncoderRef(200, 450), cn_schedule="layered")
+    assert dec._n_pruned == ref.n_pruned and np.array_equal(dec._cn_schedule, ref.schedule)
+    assert dec._cn_schedule.shape[1] == enc.z and dec.num_cns % enc.z == 0
+
+
+def test_decoder_argument_checks():
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder, LDPCBPDecoder
+    pcm = np.array([[1, 1, 0], [0, 1, 1]], dtype=np.float64)
+    with pytest.raises(TypeError):
+        LDPCBPDecoder(pcm, hard_out=1)
+    with pytest.raises(ValueError):
+        LDPCBPDecoder(pcm, num_iter=-1)
+    with pytest.raises(TypeError):
+        LDPCBPDecoder(pcm, cn_update="nope")
+    with pytest.raises(ValueError):
+        LDPCBPDecoder(pcm * 2)
+    with pytest.raises(TypeError):
+        LDPCBPDecoder(pcm, cn_type="boxplus")
+    with pytest.raises(ValueError):
+        LDPCBPDecoder(pcm, cn_schedule=np.array([[0, 5]]))
+    with pytest.raises(TypeError):
+        LDPC5GDecoder(pcm)
+    with pytest.raises(ValueError):
+        LDPC5GEncoder(8449, 10000)
+    with pytest.raises(ValueError):
+        LDPC5GEncoder(100, 1000)
+    d = LDPCBPDecoder(sp.csr_matrix(pcm))
+    d.num_iter = 3
+    d.llr_max = 10
+    assert d.num_iter == 3 and d.llr_max == 10.0 and d.num_edges == 4 and d.coderate == pytest.approx(1 / 3)
+    with pytest.raises(AssertionError):
+        d.build((5, 4))
+
+
+def test_constellation_host_side():
+    from sionna_b200.phy.mapping import Constellation, qam, pam
+    from oracle import mapping as M
+    for m in (2, 4, 6, 8):
+        assert np.array_equal(qam(m), M.qam(m))
+    assert np.array_equal(pam(3), M.pam(3))
+    c = Constellation("qam", 4)
+    assert c.num_points == 16 and c.points.shape == (16,)
+    with pytest.raises(ValueError):
+        Constellation("qam", 3)
+    with pytest.raises(ValueError):
+        Constellation("custom", 2)
+    with pytest.raises(ValueError):
+        c.points = np.zeros(16)
+
+
+def test_ebnodb2no_matches_oracle():
+    from sionna_b200.phy.utils import ebnodb2no, hard_decisions
+    from oracle import mapping as M
+    import torch
+    for e in (0.0, 2.0, 4.5):
+        assert float(ebnodb2no(e, 2, 0.5)) == float(M.ebnodb2no(e, 2, 0.5))
+    assert torch.equal(hard_decisions(torch.tensor([-1.0, 0.0, 3.0])), torch.tensor([0.0, 0.0, 1.0]))
