@@ -73,6 +73,14 @@ int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, in
                          const int32_t* h_out_vn, int32_t n_out,
                          const int32_t* h_schedule, int32_t n_sub, int32_t n_active);
 void sb_ldpc_graph_destroy(sb_ldpc_graph* g);
+/* Optional: declare the graph quasi-cyclic (lifted base graph, fec/ldpc/encoding.py:322-352): n_entries base entries
+ * (h_base_row, h_base_col, h_shift) with lifting size Z, meaning CN r*Z+i is connected to VN c*Z+(i+s) mod Z. Entries
+ * beyond the (possibly pruned) graph are ignored. The description is verified against the edge list given at
+ * creation (SB_EINVAL on mismatch, handle unchanged). Qualifying decodes (flooding, "sum" VN rule, no input state,
+ * graph fits in shared memory) then run the index-free QC kernel; results are identical either way. */
+int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entries, const int32_t* h_base_row,
+                         const int32_t* h_base_col, const int32_t* h_shift);
+int sb_ldpc_graph_is_qc(const sb_ldpc_graph* g);
 /* 1 if one codeword's messages + channel LLRs fit in one SM's shared memory (the on-chip path),
  * 0 if the decoder will keep messages in an L2-resident global workspace. */
 int sb_ldpc_graph_on_chip(const sb_ldpc_graph* g);

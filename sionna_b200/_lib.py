@@ -22,6 +22,8 @@ SIGNATURES = {
     "sb_launch_count": (i64, []),
     "sb_ldpc_graph_create": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32]),
     "sb_ldpc_graph_destroy": (None, [vp]),
+    "sb_ldpc_graph_set_qc": (i32, [vp, i32, i32, vp, vp, vp]),
+    "sb_ldpc_graph_is_qc": (i32, [vp]),
     "sb_ldpc_graph_on_chip": (i32, [vp]),
     "sb_ldpc_workspace_bytes": (sz, [vp]),
     "sb_ldpc_decode": (i32, [vp, vp, i64, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]),

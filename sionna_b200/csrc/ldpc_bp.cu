@@ -27,6 +27,7 @@
 #include <vector>
 #include "sb_common.h"
 #include "sb_math.h"
+#include "ldpc_graph.h"
 
 namespace {
 
@@ -51,34 +52,6 @@ struct BpParams {
     float offset, llr_max;
     float* ws;
 };
-
-__device__ __forceinline__ float clipf(float x, float c) { return fminf(fmaxf(x, -c), c); }
-
-// ---- mbarrier / TMA bulk-copy helpers (cp.async.bulk, 1-D) ------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // ---- check-node updates: v2c -> c2v for the CN with rank r (deg edges at slots off[l] + r) -----------
 // boxplus-phi, decoding.py:1126-1166
@@ -364,20 +337,6 @@ __global__ void __launch_bounds__(1024, 1) ldpc_bp_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------
 // Host side: graph plan (pure host), lazy upload, launch.
 // ------------------------------------------------------------------------------------------------------
-struct sb_ldpc_graph {
-    int C = 0, N = 0, E = 0, Lc = 0, Lv = 0, n_in = 0, n_out = 0, n_sub = 1, n_active = 0;
-    bool flooding = true;
-    std::vector<int> cn_off, cn_cnt, vn_off, vn_cnt, in_idx, out_pos, slot_of_edge, sched, cn_order, vn_order;
-    std::vector<uint32_t> vn_slot;
-    // device copies (lazy)
-    bool uploaded = false;
-    int device = -1;
-    int *d_cn_off = nullptr, *d_cn_cnt = nullptr, *d_vn_off = nullptr, *d_vn_cnt = nullptr, *d_in_idx = nullptr,
-        *d_out_pos = nullptr, *d_slot_of_edge = nullptr, *d_sched = nullptr;
-    uint16_t* d_vn_slot16 = nullptr;
-    uint32_t* d_vn_slot32 = nullptr;
-    int smem_optin = 0, num_sms = 0;
-};
 
 static size_t bp_smem_bytes(const sb_ldpc_graph* g, bool smem_msgs) {
     size_t arrays = g->flooding ? 1 : 2;
@@ -394,6 +353,7 @@ extern "C" int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t
                  "sb_ldpc_graph_create: bad sizes/pointers");
     auto* g = new sb_ldpc_graph();
     g->C = num_cn; g->N = num_vn; g->E = num_edges;
+    g->h_cn.assign(h_cn, h_cn + num_edges); g->h_vn.assign(h_vn, h_vn + num_edges);
     const int C = num_cn, N = num_vn, E = num_edges;
     std::vector<int> cdeg(C, 0), vdeg(N, 0);
     for (int e = 0; e < E; ++e) {
@@ -489,6 +449,7 @@ static void free_device(sb_ldpc_graph* g) {
 extern "C" void sb_ldpc_graph_destroy(sb_ldpc_graph* g) {
     if (!g) return;
     free_device(g);
+    sb_qc_free_device(g);
     delete g;
 }
 
@@ -525,8 +486,6 @@ static int ensure_uploaded(sb_ldpc_graph* g) {
     return SB_OK;
 }
 
-// B200 (sm_100) opt-in shared memory per block; used for planning when no device is present.
-static const int kSmemOptinB200 = 232448;
 
 static bool graph_on_chip(const sb_ldpc_graph* g, int smem_optin) {
     return g->E <= 65535 && bp_smem_bytes(g, true) <= (size_t)smem_optin;
@@ -585,6 +544,12 @@ extern "C" int sb_ldpc_decode(const sb_ldpc_graph* gc, const float* d_llr, int64
     auto* g = const_cast<sb_ldpc_graph*>(gc);
     int rc = ensure_uploaded(g);
     if (rc) return rc;
+    {   // quasi-cyclic fast path (ldpc_bp_qc.cu) when the graph carries a QC description and the call qualifies
+        bool handled = false;
+        rc = sb_qc_try_decode(g, d_llr, batch, num_iter, cn_rule, vn_rule, offset, llr_max, hard_out, d_state_in,
+                              d_state_out, d_out, (cudaStream_t)stream, &handled);
+        if (rc || handled) return rc;
+    }
     const bool on_chip = graph_on_chip(g, g->smem_optin);
     BpParams p{};
     p.C = g->C; p.N = g->N; p.E = g->E; p.Lc = g->Lc; p.Lv = g->Lv;

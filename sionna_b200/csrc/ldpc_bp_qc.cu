@@ -1,0 +1,534 @@
+// ldpc_bp_qc.cu -- belief-propagation fast path for quasi-cyclic (5G NR) decoding graphs on sm_100a.
+//
+// Same algorithm, arithmetic and results as ldpc_bp.cu (one CTA per codeword, messages resident in shared memory,
+// in-place flooding; reference: /root/reference/src/sionna/phy/fec/ldpc/decoding.py:416-637, 681-1166) but the
+// quasi-cyclic structure of the lifted base graph (encoding.py:322-352: every base entry (r, c, s) is a ZxZ identity
+// shifted by s) replaces every index table by arithmetic:
+//   * message slot of base entry `be` and check offset i (CN = r*Z + i):   be*Z + i
+//     - CN (r, i) walks its edges with a constant stride of Z words: no loads of indices at all;
+//     - VN (c, j) reaches the edge of entry (r, c, s) at be*Z + ((j - s) mod Z): one broadcast LDS of a packed
+//       table word + 4 integer ops; 32 consecutive VNs hit 32 consecutive words (mod the wrap): conflict free.
+//   * a warp owns 32 consecutive checks (or variables) of ONE base row (column): degree and table entries are
+//     warp-uniform, so the min-sum update keeps the whole row in registers (fully unrolled degree buckets, one
+//     shared-memory read and one write per edge) and the VN update keeps addresses + messages in registers.
+//   * rows / columns are processed in order of decreasing degree, dealt cyclically to the warps (load balance).
+// Partial trailing blocks (pruned graphs whose size is not a multiple of Z) are handled with per-entry limits.
+// Summation orders (ascending VN inside a CN, ascending CN inside a VN) are those of ldpc_bp.cu, so both kernels
+// and the CPU oracle (math_mode 1, order "kernel") agree bit for bit.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+#include "sb_common.h"
+#include "sb_math.h"
+#include "ldpc_graph.h"
+
+namespace {
+
+struct QcParams {
+    int Z, n_rows, n_cols, nnz, N, E, E_alloc, n_in, n_out;
+    const int2* row_info;    // {first base entry, deg | zrow << 16}, processing order
+    const int4* col_info;    // {first col-edge, deg | check << 16, zcol, c*Z}, processing order
+    const int2* col_edge;    // {be*Z*4, s*4 | (zrow*4) << 16}, ascending base row inside a column
+    const int* in_idx;       // [N] natural VN order
+    const int* out_pos;      // [N]
+    const int* slot_of_edge; // [E] reference edge -> slot
+    const float* llr;
+    float* out;
+    float* state_out;
+    long long B;
+    int num_iter, hard_out, use_tma;
+    float offset, llr_max;
+};
+
+// phi with the argument already clamped by the caller's domain: identical results to sb_phif (the range checks
+// of sb_expf never fire for x in [8.5e-8, 16.635532]).
+__device__ __forceinline__ float phi_dev(float x) { return sb_phif(x); }
+
+// ---- check-node updates on the edges pm[0], pm[Z], pm[2Z], ... of one check ------------------------------------
+__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip) {
+    float P = 0.f;
+    unsigned par = 0;
+#pragma unroll 4
+    for (int l = 0; l < deg; ++l) {
+        float* q = pm + l * Z;
+        float v = __fadd_rn(*q, 0.f);                     // -0 -> +0: afterwards sign bit <=> v < 0 (sign(0) := +1)
+        unsigned b = __float_as_uint(v);
+        par ^= b;
+        float p = phi_dev(fabsf(v));                      // >= 0 (tests/test_sb_math.py)
+        P = __fadd_rn(P, p);
+        *q = __uint_as_float(__float_as_uint(p) | (b & 0x80000000u));
+    }
+    par &= 0x80000000u;
+#pragma unroll 4
+    for (int l = 0; l < deg; ++l) {
+        float* q = pm + l * Z;
+        unsigned b = __float_as_uint(*q);
+        float p = __uint_as_float(b & 0x7fffffffu);
+        float y = fminf(phi_dev(__fadd_rn(-p, P)), clip); // clip(s*y) == s*min(y, clip) for y >= 0
+        *q = __uint_as_float(__float_as_uint(y) | ((b ^ par) & 0x80000000u));
+    }
+}
+
+__device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip) {
+    const float atanh_clip = (float)(1 - 1e-7);
+    float prod = 1.f;
+#pragma unroll 2
+    for (int l = 0; l < deg; ++l) {
+        float* q = pm + l * Z;
+        float t = sb_tanhf(__fmul_rn(*q, 0.5f));
+        if (t == 0.f) t = 1e-12f;
+        prod = __fmul_rn(prod, t);
+        *q = t;
+    }
+#pragma unroll 2
+    for (int l = 0; l < deg; ++l) {
+        float* q = pm + l * Z;
+        float e = __fmul_rn(__fdiv_rn(1.f, *q), prod);
+        if (fabsf(e) < 1e-7f) e = 0.f;
+        e = clipf(e, atanh_clip);
+        *q = clipf(__fmul_rn(2.f, sb_atanhf(e)), clip);
+    }
+}
+
+// (offset-)min-sum with the row in registers. Preconditions checked on the host: |message| <= llr_max and
+// (deg-1)*llr_max < 99000, so the reference's 1e5 sentinel logic (decoding.py:849-887) reduces exactly to
+//   unique minimum -> that edge gets fl(fl(m2 - m1) + m1), all others m1;  repeated minimum -> all edges m1.
+// Offset, max(.,0) and clipping act on only two distinct magnitudes and are hoisted out of the edge loop.
+template <int DMAX>
+__device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset) {
+    float x[DMAX];                                        // every element is assigned unconditionally (registers)
+    float m1 = INFINITY, m2 = INFINITY;
+    unsigned par = 0;
+#pragma unroll
+    for (int l = 0; l < DMAX; ++l) {
+        const bool on = l < deg;                          // warp-uniform
+        float v = INFINITY;                               // neutral: never the minimum, sign +
+        if (on) v = __fadd_rn(pm[l * Z], 0.f);
+        x[l] = v;
+        float a = fabsf(v);
+        m2 = fminf(m2, fmaxf(m1, a));
+        m1 = fminf(m1, a);
+        par ^= __float_as_uint(v);
+    }
+    par &= 0x80000000u;
+    float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
+    if (deg == 1) min_e = __fadd_rn(100000.f, m1);
+    const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
+    const float oe = fminf(fmaxf(__fsub_rn(min_e, offset), 0.f), clip);
+#pragma unroll
+    for (int l = 0; l < DMAX; ++l) {
+        float v = x[l];
+        float mag = (fabsf(v) == m1) ? oe : o1;
+        float y = __uint_as_float(__float_as_uint(mag) | ((__float_as_uint(v) ^ par) & 0x80000000u));
+        if (l < deg) pm[l * Z] = y;
+    }
+}
+
+// generic-degree fallback (re-reads shared memory instead of holding the row in registers)
+__device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, float clip, float offset) {
+    float m1 = INFINITY, m2 = INFINITY;
+    unsigned par = 0;
+    for (int l = 0; l < deg; ++l) {
+        float v = __fadd_rn(pm[l * Z], 0.f);
+        float a = fabsf(v);
+        m2 = fminf(m2, fmaxf(m1, a));
+        m1 = fminf(m1, a);
+        par ^= __float_as_uint(v);
+    }
+    par &= 0x80000000u;
+    float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
+    if (deg == 1) min_e = __fadd_rn(100000.f, m1);
+    const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
+    const float oe = fminf(fmaxf(__fsub_rn(min_e, offset), 0.f), clip);
+    for (int l = 0; l < deg; ++l) {
+        float v = __fadd_rn(pm[l * Z], 0.f);
+        float mag = (fabsf(v) == m1) ? oe : o1;
+        pm[l * Z] = __uint_as_float(__float_as_uint(mag) | ((__float_as_uint(v) ^ par) & 0x80000000u));
+    }
+}
+
+template <int RULE>
+__device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset) {
+    if (RULE == SB_CN_BOXPLUS_PHI) cn_phi_qc(pm, Z, deg, clip);
+    else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
+    else {
+        const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
+        if (deg <= 4) cn_minsum_qc<4>(pm, Z, deg, clip, off);
+        else if (deg <= 8) cn_minsum_qc<8>(pm, Z, deg, clip, off);
+        else if (deg <= 12) cn_minsum_qc<12>(pm, Z, deg, clip, off);
+        else if (deg <= 20) cn_minsum_qc<20>(pm, Z, deg, clip, off);
+        else cn_minsum_qc_loop(pm, Z, deg, clip, off);
+    }
+}
+
+// ---- variable-node update (decoding.py:714-732) for VN (c, j); msgb = message array as bytes -----------------
+// Returns the unclipped x_tot. MODE 0: normal update; MODE 1: initialisation v2c = llr (decoding.py:571).
+template <int DMAX, bool CHECK, bool KEEPM, int MODE>
+__device__ __forceinline__ float vn_qc(char* msgb, const int2* ce, int deg, int j4, int Z4, float llr, float clip) {
+    int addr[DMAX];                                       // assigned unconditionally so the arrays stay in registers
+    float m[KEEPM ? DMAX : 1];
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        int a = -1;
+        float v = 0.f;
+        if (k < deg) {                                    // warp-uniform
+            int2 e = ce[k];
+            int t = j4 - (e.y & 0xffff);
+            t += (t >> 31) & Z4;                          // (j - s) mod Z, in bytes
+            bool ok = !CHECK || t < (int)((unsigned)e.y >> 16);   // edge exists (row not cut by pruning)
+            if (ok) {
+                a = e.x + t;
+                if (MODE == 0) {
+                    v = *reinterpret_cast<float*>(msgb + a);
+                    acc = __fadd_rn(acc, v);              // :715 sequential, ascending CN
+                }
+            }
+        }
+        addr[k] = a;
+        if (KEEPM) m[k] = v;
+    }
+    float x_tot = __fadd_rn(acc, llr);                    // :716
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        int a = addr[k];
+        if (k < deg && (!CHECK || a >= 0)) {
+            float* q = reinterpret_cast<float*>(msgb + a);
+            if (MODE == 1) *q = llr;
+            else {
+                float v = KEEPM ? m[KEEPM ? k : 0] : *q;
+                *q = clipf(__fadd_rn(-v, x_tot), clip);    // :724-729
+            }
+        }
+    }
+    return x_tot;
+}
+
+template <int MODE>
+__device__ __forceinline__ float vn_qc_loop(char* msgb, const int2* ce, int deg, int j4, int Z4, float llr, float clip) {
+    float acc = 0.f;
+    if (MODE == 0)
+        for (int k = 0; k < deg; ++k) {
+            int2 e = ce[k];
+            int t = j4 - (e.y & 0xffff);
+            t += (t >> 31) & Z4;
+            if (t < (int)((unsigned)e.y >> 16)) acc = __fadd_rn(acc, *reinterpret_cast<float*>(msgb + e.x + t));
+        }
+    float x_tot = __fadd_rn(acc, llr);
+    for (int k = 0; k < deg; ++k) {
+        int2 e = ce[k];
+        int t = j4 - (e.y & 0xffff);
+        t += (t >> 31) & Z4;
+        if (t < (int)((unsigned)e.y >> 16)) {
+            float* q = reinterpret_cast<float*>(msgb + e.x + t);
+            *q = (MODE == 1) ? llr : clipf(__fadd_rn(-*q, x_tot), clip);
+        }
+    }
+    return x_tot;
+}
+
+template <int MODE>
+__device__ __forceinline__ float vn_dispatch(char* msgb, const int2* ce, int deg, bool check, int j4, int Z4, float llr,
+                                             float clip) {
+    if (!check) {
+        if (deg <= 2) return vn_qc<2, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 4) return vn_qc<4, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 8) return vn_qc<8, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 12) return vn_qc<12, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 20) return vn_qc<20, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 32) return vn_qc<32, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    } else {
+        if (deg <= 4) return vn_qc<4, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (deg <= 12) return vn_qc<12, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    }
+    return vn_qc_loop<MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int Z = p.Z, Z4 = 4 * Z, N = p.N, Zb = (Z + 31) >> 5;
+    // carve-up by byte offsets from the __shared__ base (keeps the shared address space visible to the compiler)
+    const int off_llr = p.E_alloc * 4;
+    const int off_col = (off_llr + N * 4 + 15) & ~15;
+    const int off_row = off_col + p.n_cols * 16;
+    const int off_ce = off_row + p.n_rows * 8;
+    const int off_bar = (off_ce + p.nnz * 8 + 15) & ~15;
+    float* msg = reinterpret_cast<float*>(smem_raw);
+    float* llr_s = reinterpret_cast<float*>(smem_raw + off_llr);
+    int4* s_col = reinterpret_cast<int4*>(smem_raw + off_col);
+    int2* s_row = reinterpret_cast<int2*>(smem_raw + off_row);
+    int2* s_ce = reinterpret_cast<int2*>(smem_raw + off_ce);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
+    char* msgb = reinterpret_cast<char*>(smem_raw);
+    // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
+    const int G = W / Zb, grp = warp / Zb, ib = warp - grp * Zb;
+    const bool warp_used = warp < G * Zb;
+    const int lane_i = ib * 32 + lane;
+
+    for (int i = tid; i < p.n_cols; i += T) s_col[i] = p.col_info[i];
+    for (int i = tid; i < p.n_rows; i += T) s_row[i] = p.row_info[i];
+    for (int i = tid; i < p.nnz; i += T) s_ce[i] = p.col_edge[i];
+    if (p.use_tma && tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const float clip = p.llr_max;
+    uint32_t tma_phase = 0;
+
+    for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+        // ---- channel LLRs (decoding.py:552-565, 1444-1475), natural VN order -----------------------------------
+        const float* row = p.llr + (size_t)b * p.n_in;
+        if (p.use_tma) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, (uint32_t)p.n_in * 4u);
+                tma_bulk_g2s(msg, row, (uint32_t)p.n_in * 4u, bar);
+            }
+            mbar_wait(bar, tma_phase);
+            tma_phase ^= 1u;
+            for (int v = tid; v < N; v += T) {
+                int ii = p.in_idx[v];
+                float l = ii >= 0 ? msg[ii] : (ii == -1 ? 0.f : -clip);
+                llr_s[v] = __fmul_rn(clipf(l, clip), -1.f);
+            }
+        } else {
+            for (int v = tid; v < N; v += T) {
+                int ii = p.in_idx[v];
+                float l = ii >= 0 ? __ldg(row + ii) : (ii == -1 ? 0.f : -clip);
+                llr_s[v] = __fmul_rn(clipf(l, clip), -1.f);
+            }
+        }
+        __syncthreads();
+        // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
+        if (warp_used)
+            for (int cc = grp; cc < p.n_cols; cc += G) {
+                int4 ci = s_col[cc];
+                if (lane_i < ci.z)
+                    vn_dispatch<1>(msgb, s_ce + ci.x, ci.y & 0xffff, (ci.y >> 16) != 0, 4 * lane_i, Z4,
+                                   llr_s[ci.w + lane_i], clip);
+            }
+        __syncthreads();
+        if (p.num_iter == 0) {
+            for (int v = tid; v < N; v += T) {
+                int o = p.out_pos[v];
+                if (o >= 0) {
+                    float x = llr_s[v];
+                    p.out[(size_t)b * p.n_out + o] = p.hard_out ? (0.f >= x ? 1.f : 0.f) : __fmul_rn(x, -1.f);
+                }
+            }
+        }
+        for (int it = 0; it < p.num_iter; ++it) {
+            // ---- CN phase ---------------------------------------------------------------------------------------
+            if (warp_used)
+                for (int rr = grp; rr < p.n_rows; rr += G) {
+                    int2 ri = s_row[rr];
+                    if (lane_i < (ri.y >> 16)) cn_qc<RULE>(msg + ri.x * Z + lane_i, Z, ri.y & 0xffff, clip, p.offset);
+                }
+            __syncthreads();
+            // ---- VN phase ---------------------------------------------------------------------------------------
+            const bool final_pass = it == p.num_iter - 1;
+            if (warp_used)
+            for (int cc = grp; cc < p.n_cols; cc += G) {
+                int4 ci = s_col[cc];
+                if (lane_i < ci.z) {
+                    int v = ci.w + lane_i;
+                    float x_tot = vn_dispatch<0>(msgb, s_ce + ci.x, ci.y & 0xffff, (ci.y >> 16) != 0, 4 * lane_i, Z4,
+                                                 llr_s[v], clip);
+                    if (final_pass) {
+                        int o = p.out_pos[v];
+                        if (o >= 0) {
+                            x_tot = clipf(x_tot, clip);                                              // :730
+                            p.out[(size_t)b * p.n_out + o] = p.hard_out ? (0.f >= x_tot ? 1.f : 0.f) // :622-626
+                                                                        : __fmul_rn(x_tot, -1.f);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (p.state_out) {
+            float* st = p.state_out + (size_t)b * p.E;
+            for (int e = tid; e < p.E; e += T) st[e] = __fmul_rn(msg[p.slot_of_edge[e]], -1.f);
+            __syncthreads();
+        }
+    }
+}
+
+size_t qc_smem_bytes(const sb_ldpc_graph* g) {
+    return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 8 +
+           (size_t)g->qc_nnz * 8 + 16 + 16;
+}
+
+template <typename T>
+int upload_ints(T** d, const std::vector<T>& h) {
+    SB_CUDA(cudaMalloc((void**)d, std::max<size_t>(1, h.size()) * sizeof(T)));
+    if (h.size()) SB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SB_OK;
+}
+
+int qc_ensure_uploaded(sb_ldpc_graph* g) {
+    if (g->qc_uploaded) return SB_OK;
+    int rc;
+    if ((rc = upload_ints(&g->d_qc_row_info, g->qc_row_info))) return rc;
+    if ((rc = upload_ints(&g->d_qc_col_info, g->qc_col_info))) return rc;
+    if ((rc = upload_ints(&g->d_qc_col_edge, g->qc_col_edge))) return rc;
+    if ((rc = upload_ints(&g->d_qc_in_idx, g->qc_in_idx))) return rc;
+    if ((rc = upload_ints(&g->d_qc_out_pos, g->qc_out_pos))) return rc;
+    if ((rc = upload_ints(&g->d_qc_slot_of_edge, g->qc_slot_of_edge))) return rc;
+    g->qc_uploaded = true;
+    return SB_OK;
+}
+
+template <int RULE>
+int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = ldpc_bp_qc_kernel<RULE>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) { sb_set_error("sb_ldpc_decode(qc): kernel does not fit (threads %d, smem %zu)", threads, smem); return SB_EUNSUPPORTED; }
+    long long grid = std::min<long long>(p.B, (long long)g->num_sms * occ);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(p);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+}  // namespace
+
+void sb_qc_free_device(sb_ldpc_graph* g) {
+    if (!g->qc_uploaded) return;
+    cudaFree(g->d_qc_row_info); cudaFree(g->d_qc_col_info); cudaFree(g->d_qc_col_edge); cudaFree(g->d_qc_in_idx);
+    cudaFree(g->d_qc_out_pos); cudaFree(g->d_qc_slot_of_edge);
+    g->qc_uploaded = false;
+}
+
+// Attach the quasi-cyclic description of the graph: base entries (row, col, shift) of the lifted matrix with lifting
+// size Z; entries outside ceil(C/Z) x ceil(N/Z) are ignored (pruned away). The description is verified against the
+// handle's edge list; on mismatch the handle is left unchanged and SB_EINVAL is returned.
+extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entries, const int32_t* base_row,
+                                    const int32_t* base_col, const int32_t* shift) {
+    SB_CHECK_ARG(g && Z > 0 && Z <= 16383 && n_entries > 0 && base_row && base_col && shift, "sb_ldpc_graph_set_qc: bad arguments");
+    SB_CHECK_ARG((int)g->h_cn.size() == g->E, "sb_ldpc_graph_set_qc: handle holds no edge list");
+    const int C = g->C, N = g->N, E = g->E;
+    const int n_rows = (C + Z - 1) / Z, n_cols = (N + Z - 1) / Z;
+    auto zrow = [&](int r) { return std::min(Z, C - r * Z); };
+    auto zcol = [&](int c) { return std::min(Z, N - c * Z); };
+    struct Ent { int r, c, s; };
+    std::vector<Ent> ents;
+    for (int k = 0; k < n_entries; ++k) {
+        if (base_row[k] < 0 || base_col[k] < 0 || shift[k] < 0) { sb_set_error("sb_ldpc_graph_set_qc: negative entry"); return SB_EINVAL; }
+        if (base_row[k] >= n_rows || base_col[k] >= n_cols) continue;
+        ents.push_back({base_row[k], base_col[k], shift[k] % Z});
+    }
+    // verify against the edge list
+    std::vector<long long> keys(E);
+    for (int e = 0; e < E; ++e) keys[e] = ((long long)g->h_cn[e] << 32) | (unsigned)g->h_vn[e];
+    std::sort(keys.begin(), keys.end());
+    long long total = 0;
+    for (const Ent& en : ents)
+        for (int i = 0; i < zrow(en.r); ++i) {
+            int j = (i + en.s) % Z;
+            long long key = ((long long)(en.r * Z + i) << 32) | (unsigned)(en.c * Z + j);
+            if (j >= zcol(en.c) || !std::binary_search(keys.begin(), keys.end(), key)) {
+                sb_set_error("sb_ldpc_graph_set_qc: base entry (%d,%d,%d) does not match the graph", en.r, en.c, en.s);
+                return SB_EINVAL;
+            }
+            ++total;
+        }
+    if (total != E) { sb_set_error("sb_ldpc_graph_set_qc: %lld lifted edges != %d graph edges", total, E); return SB_EINVAL; }
+    // rows / columns by decreasing degree (stable)
+    std::vector<int> rdeg(n_rows, 0), cdeg(n_cols, 0);
+    for (const Ent& en : ents) { ++rdeg[en.r]; ++cdeg[en.c]; }
+    std::vector<int> rorder(n_rows), corder(n_cols);
+    std::iota(rorder.begin(), rorder.end(), 0);
+    std::iota(corder.begin(), corder.end(), 0);
+    std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) { return rdeg[a] > rdeg[b]; });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cdeg[a] > cdeg[b]; });
+    // base-entry numbering: rows in processing order, ascending column inside a row
+    std::vector<int> be_of((size_t)n_rows * n_cols, -1);
+    std::vector<int> row_info(2 * n_rows), shift_of(ents.size());
+    std::vector<std::vector<Ent>> by_row(n_rows), by_col(n_cols);
+    for (const Ent& en : ents) { by_row[en.r].push_back(en); by_col[en.c].push_back(en); }
+    int be = 0;
+    for (int rr = 0; rr < n_rows; ++rr) {
+        int r = rorder[rr];
+        std::sort(by_row[r].begin(), by_row[r].end(), [](const Ent& a, const Ent& b) { return a.c < b.c; });
+        row_info[2 * rr] = be;
+        row_info[2 * rr + 1] = rdeg[r] | (zrow(r) << 16);
+        for (const Ent& en : by_row[r]) {
+            if (be_of[(size_t)en.r * n_cols + en.c] != -1) { sb_set_error("sb_ldpc_graph_set_qc: duplicate base entry"); return SB_EINVAL; }
+            be_of[(size_t)en.r * n_cols + en.c] = be++;
+        }
+    }
+    const int nnz = be;
+    std::vector<int> col_info(4 * n_cols), col_edge(2 * (size_t)nnz);
+    int ce = 0;
+    for (int cc = 0; cc < n_cols; ++cc) {
+        int c = corder[cc];
+        std::sort(by_col[c].begin(), by_col[c].end(), [](const Ent& a, const Ent& b) { return a.r < b.r; });
+        bool check = false;
+        col_info[4 * cc] = ce;
+        for (const Ent& en : by_col[c]) {
+            col_edge[2 * ce] = be_of[(size_t)en.r * n_cols + en.c] * Z * 4;
+            col_edge[2 * ce + 1] = (en.s * 4) | ((zrow(en.r) * 4) << 16);
+            check = check || zrow(en.r) < Z;
+            ++ce;
+        }
+        col_info[4 * cc + 1] = cdeg[c] | ((check ? 1 : 0) << 16);
+        col_info[4 * cc + 2] = zcol(c);
+        col_info[4 * cc + 3] = c * Z;
+    }
+    // natural-order I/O maps and the reference-edge -> slot map
+    std::vector<int> in_nat(N), out_nat(N), slot(E);
+    for (int r = 0; r < N; ++r) { in_nat[g->vn_order[r]] = g->in_idx[r]; out_nat[g->vn_order[r]] = g->out_pos[r]; }
+    for (int e = 0; e < E; ++e) {
+        int r = g->h_cn[e] / Z, i = g->h_cn[e] % Z, c = g->h_vn[e] / Z;
+        slot[e] = be_of[(size_t)r * n_cols + c] * Z + i;
+    }
+    sb_qc_free_device(g);
+    g->qc = true; g->qc_Z = Z; g->qc_rows = n_rows; g->qc_cols = n_cols; g->qc_nnz = nnz;
+    g->qc_max_row_deg = *std::max_element(rdeg.begin(), rdeg.end());
+    g->qc_max_col_deg = *std::max_element(cdeg.begin(), cdeg.end());
+    g->qc_row_info.swap(row_info); g->qc_col_info.swap(col_info); g->qc_col_edge.swap(col_edge);
+    g->qc_in_idx.swap(in_nat); g->qc_out_pos.swap(out_nat); g->qc_slot_of_edge.swap(slot);
+    return SB_OK;
+}
+
+extern "C" int sb_ldpc_graph_is_qc(const sb_ldpc_graph* g) { return g && g->qc ? 1 : 0; }
+
+int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_t num_iter, int32_t cn_rule,
+                     int32_t vn_rule, float offset, float llr_max, int32_t hard_out, const float* d_state_in,
+                     float* d_state_out, float* d_out, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (!g->qc || !g->flooding || vn_rule != SB_VN_SUM || d_state_in || cn_rule > SB_CN_OFFSET_MINSUM) return SB_OK;
+    const size_t smem = qc_smem_bytes(g);
+    if (smem > (size_t)g->smem_optin) return SB_OK;
+    if ((cn_rule == SB_CN_MINSUM || cn_rule == SB_CN_OFFSET_MINSUM) &&
+        !(llr_max < 100000.f && (float)(g->qc_max_row_deg - 1) * llr_max < 99000.f))
+        return SB_OK;                                      // the generic kernel has the literal 1e5-sentinel path
+    int rc = qc_ensure_uploaded(g);
+    if (rc) return rc;
+    QcParams p{};
+    p.Z = g->qc_Z; p.n_rows = g->qc_rows; p.n_cols = g->qc_cols; p.nnz = g->qc_nnz; p.N = g->N; p.E = g->E;
+    p.E_alloc = g->qc_nnz * g->qc_Z; p.n_in = g->n_in; p.n_out = g->n_out;
+    p.row_info = (const int2*)g->d_qc_row_info; p.col_info = (const int4*)g->d_qc_col_info;
+    p.col_edge = (const int2*)g->d_qc_col_edge; p.in_idx = g->d_qc_in_idx; p.out_pos = g->d_qc_out_pos;
+    p.slot_of_edge = g->d_qc_slot_of_edge;
+    p.llr = d_llr; p.out = d_out; p.state_out = d_state_out; p.B = batch; p.num_iter = num_iter; p.hard_out = hard_out;
+    p.offset = offset; p.llr_max = llr_max;
+    p.use_tma = (g->n_in % 4 == 0) && (g->n_in <= p.E_alloc) && ((reinterpret_cast<uintptr_t>(d_llr) & 15) == 0);
+    const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
+    int groups = std::max(1, std::min(24 / Zb, std::max(g->qc_rows, g->qc_cols)));
+    const int threads = groups * Zb * 32;                  // every warp owns one slice index for the whole launch
+    switch (cn_rule) {
+        case SB_CN_BOXPLUS_PHI: rc = launch_qc<SB_CN_BOXPLUS_PHI>(g, p, threads, smem, stream); break;
+        case SB_CN_BOXPLUS: rc = launch_qc<SB_CN_BOXPLUS>(g, p, threads, smem, stream); break;
+        case SB_CN_MINSUM: rc = launch_qc<SB_CN_MINSUM>(g, p, threads, smem, stream); break;
+        default: rc = launch_qc<SB_CN_OFFSET_MINSUM>(g, p, threads, smem, stream); break;
+    }
+    *handled = (rc == SB_OK);
+    return rc;
+}

@@ -8,6 +8,7 @@ codeword with the codeword's edge messages resident in shared memory for every i
 index maps, so the decoder moves 4*n bytes in and 4*k (or 4*n) bytes out per codeword and nothing else.
 """
 import ctypes as C
+import os
 import types
 import numpy as np
 import scipy as sp
@@ -52,6 +53,14 @@ class _GraphHandle:
 
     def on_chip(self):
         return bool(lib().sb_ldpc_graph_on_chip(self._h))
+
+    def set_qc(self, z, base_row, base_col, shift):
+        """Declare the lifted-base-graph structure (enables the index-free QC kernel); returns False if rejected."""
+        r, c, s = _i32(base_row), _i32(base_col), _i32(shift)
+        return lib().sb_ldpc_graph_set_qc(self._h, int(z), len(r), ptr(r), ptr(c), ptr(s)) == 0
+
+    def is_qc(self):
+        return bool(lib().sb_ldpc_graph_is_qc(self._h))
 
     def workspace(self, device):
         need = lib().sb_ldpc_workspace_bytes(self._h)
@@ -334,6 +343,10 @@ class LDPC5GDecoder(LDPCBPDecoder):
                          cn_schedule=cn_schedule, hard_out=hard_out, num_iter=num_iter, llr_max=llr_max,
                          v2c_callbacks=v2c_callbacks, c2v_callbacks=c2v_callbacks, return_state=return_state,
                          precision=precision, **kwargs)
+        # the decoding graph is a (possibly truncated) lifted base graph: let the C side use its QC fast path
+        if os.environ.get("SB_LDPC_DISABLE_QC", "0") != "1":
+            br, bc = np.nonzero(encoder._bm >= 0)
+            self._graph.set_qc(encoder.z, br, bc, encoder._bm[br, bc] % encoder.z)
 
     @property
     def encoder(self):

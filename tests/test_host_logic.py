@@ -142,3 +142,19 @@ def test_ebnodb2no_matches_oracle():
     for e in (0.0, 2.0, 4.5):
         assert float(ebnodb2no(e, 2, 0.5)) == float(M.ebnodb2no(e, 2, 0.5))
     assert torch.equal(hard_decisions(torch.tensor([-1.0, 0.0, 3.0])), torch.tensor([0.0, 0.0, 1.0]))
+
+
+def test_qc_description_accepted_and_rejected():
+    """sb_ldpc_graph_set_qc verifies the lifted base graph against the edge list (host only, no GPU)."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    for k, n in ((100, 200), (562, 871), (4224, 8448)):      # (562, 871): pruned size is not a multiple of Z
+        enc = LDPC5GEncoder(k, n)
+        dec = LDPC5GDecoder(enc)
+        assert dec._graph.is_qc()
+        br, bc = np.nonzero(enc._bm >= 0)
+        sh = enc._bm[br, bc] % enc.z
+        bad = sh.copy()
+        bad[3] = (bad[3] + 1) % enc.z
+        assert not dec._graph.set_qc(enc.z, br, bc, bad)      # wrong shift -> rejected, handle keeps the valid one
+        assert dec._graph.is_qc()
+        assert not dec._graph.set_qc(enc.z, br[:-1], bc[:-1], sh[:-1]) or dec.num_cns < 46 * enc.z

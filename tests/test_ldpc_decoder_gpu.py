@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 RULES = ["boxplus-phi", "boxplus", "minsum", "offset-minsum"]
 
 
+@pytest.fixture(params=["qc", "generic"])
+def kernel_path(request, monkeypatch):
+    """5G graphs run either the index-free QC kernel (default) or, with SB_LDPC_DISABLE_QC=1, the generic one."""
+    monkeypatch.setenv("SB_LDPC_DISABLE_QC", "0" if request.param == "qc" else "1")
+    return request.param
+
+
 def _noisy_llr(c, ebno_db, rate, rng):
     """BPSK over AWGN: logits log p(1)/p(0) for codeword bits c."""
     no = 1.0 / (10 ** (ebno_db / 10) * rate)
@@ -54,8 +61,8 @@ def test_generic_pcm_bit_exact(cuda_device, rule, pcm_id):
 
 
 @pytest.mark.parametrize("rule", RULES)
-@pytest.mark.parametrize("k,n", [(64, 128), (100, 200), (562, 871), (1024, 2048), (4224, 8448)])
-def test_5g_bit_exact(cuda_device, rule, k, n):
+@pytest.mark.parametrize("k,n", [(64, 128), (100, 200), (562, 871), (1024, 2048), (1500, 2000), (4224, 8448)])
+def test_5g_bit_exact(cuda_device, kernel_path, rule, k, n):
     from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
     rng = np.random.default_rng(k + n)
     enc_r = O.LDPC5GEncoderRef(k, n)
@@ -66,7 +73,7 @@ def test_5g_bit_exact(cuda_device, rule, k, n):
     enc = LDPC5GEncoder(k, n)
     for hard, info in ((True, True), (False, False)):
         dec = LDPC5GDecoder(enc, cn_update=rule, hard_out=hard, return_infobits=info, num_iter=10, return_state=True)
-        assert dec.on_chip
+        assert dec.on_chip and dec._graph.is_qc() == (kernel_path == "qc")
         x, st = dec(torch.from_numpy(llr).to(cuda_device))
         ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=hard, return_infobits=info, num_iter=10,
                                  return_state=True)
@@ -75,7 +82,7 @@ def test_5g_bit_exact(cuda_device, rule, k, n):
         assert np.array_equal(st.cpu().numpy(), str_)
 
 
-def test_5g_interleaver_and_no_pruning(cuda_device):
+def test_5g_interleaver_and_no_pruning(cuda_device, kernel_path):
     from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
     rng = np.random.default_rng(7)
     k, n, m = 300, 720, 6
@@ -124,7 +131,7 @@ def test_large_graph_global_workspace_path(cuda_device):
     assert np.array_equal(x, ref(llr, math_mode=1, order="kernel"))
 
 
-def test_state_handover_and_multidim(cuda_device):
+def test_state_handover_and_multidim(cuda_device, kernel_path):
     """1 x N iterations == N x 1 iteration with state hand-over (test_ldpc_decoding.py:875-911); [..., n] batches."""
     from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
     rng = np.random.default_rng(3)
@@ -145,7 +152,7 @@ def test_state_handover_and_multidim(cuda_device):
     assert float(s5.abs().max()) <= 20.0 and float(x5.abs().max()) <= 20.0
 
 
-def test_vs_libm_oracle(cuda_device):
+def test_vs_libm_oracle(cuda_device, kernel_path):
     """Against the oracle's glibc-libm / reference-order mode (the stand-in for TF's own libm): after ONE iteration
     soft outputs agree to rtol 1e-4 (north-star LLR tolerance) for every rule; after 20 iterations at 2 dB the
     decoded bits agree."""
@@ -166,3 +173,21 @@ def test_vs_libm_oracle(cuda_device):
         ur = O.LDPC5GDecoderRef(enc_r, cn_update=rule, num_iter=20)(llr)
         assert np.mean(ub != ur) < 1e-3
         assert np.mean(ub != u) < 1e-2
+
+
+def test_qc_zero_iterations_and_large_llr_max(cuda_device):
+    """num_iter = 0 returns the clipped channel logits; llr_max so large that min-sum must take the generic kernel's
+    literal 1e5-sentinel path still matches the oracle."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    rng = np.random.default_rng(9)
+    k, n = 400, 800
+    enc, enc_r = LDPC5GEncoder(k, n), O.LDPC5GEncoderRef(k, n)
+    llr = (rng.normal(size=(12, n)) * 8).astype(np.float32)
+    x = LDPC5GDecoder(enc, hard_out=False, return_infobits=False, num_iter=0)(torch.from_numpy(llr).to(cuda_device))
+    assert np.array_equal(x.cpu().numpy(), np.clip(llr, -20, 20))
+    big = (rng.normal(size=(12, n)) * 4e4).astype(np.float32)
+    for rule in ("minsum", "offset-minsum"):
+        dec = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, num_iter=3, llr_max=90000.0)
+        ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=False, num_iter=3, llr_max=90000.0)
+        assert np.array_equal(dec(torch.from_numpy(big).to(cuda_device)).cpu().numpy(),
+                              ref(big, math_mode=1, order="kernel"))
