@@ -81,6 +81,9 @@ void sb_ldpc_graph_destroy(sb_ldpc_graph* g);
 int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entries, const int32_t* h_base_row,
                          const int32_t* h_base_col, const int32_t* h_shift);
 int sb_ldpc_graph_is_qc(const sb_ldpc_graph* g);
+/* Test hook: phi(x) of decoding.py:1110-1120 evaluated on the device by the scalar and by the packed-fp32x2 code path
+ * (n even); both must equal the CPU oracle bit for bit. */
+int sb_debug_phi(const float* d_x, float* d_scalar, float* d_packed, int64_t n, void* stream);
 /* 1 if one codeword's messages + channel LLRs fit in one SM's shared memory (the on-chip path),
  * 0 if the decoder will keep messages in an L2-resident global workspace. */
 int sb_ldpc_graph_on_chip(const sb_ldpc_graph* g);

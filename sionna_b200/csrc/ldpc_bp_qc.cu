@@ -20,14 +20,22 @@
 #include <vector>
 #include "sb_common.h"
 #include "sb_math.h"
+#include "sb_math2.cuh"
 #include "ldpc_graph.h"
 
 namespace {
 
+constexpr int kRowClasses = 5;    // CN degree classes, heaviest first: >20 (loop), <=20, <=12, <=8, <=4
+constexpr int kColClasses = 11;   // VN classes, see col_class() on the host side
+
 struct QcParams {
     int Z, n_rows, n_cols, nnz, N, E, E_alloc, n_in, n_out;
-    const int2* row_info;    // {first base entry, deg | zrow << 16}, processing order
-    const int4* col_info;    // {first col-edge, deg | check << 16, zcol, c*Z}, processing order
+    int row_cls_end[kRowClasses];   // processing order: rows of class k are [row_cls_end[k-1], row_cls_end[k])
+    int col_cls_end[kColClasses];
+    int row_cls_mod[kRowClasses];   // (first index of class k) mod G, G = warp groups of this launch
+    int col_cls_mod[kColClasses];
+    const int4* row_info;    // {first base entry, deg, zrow, fused VN base (c*Z | s << 16... see host) or -1}
+    const int4* col_info;    // {first col-edge, deg, zcol, c*Z}
     const int2* col_edge;    // {be*Z*4, s*4 | (zrow*4) << 16}, ascending base row inside a column
     const int* in_idx;       // [N] natural VN order
     const int* out_pos;      // [N]
@@ -40,32 +48,55 @@ struct QcParams {
     float offset, llr_max;
 };
 
-// phi with the argument already clamped by the caller's domain: identical results to sb_phif (the range checks
-// of sb_expf never fire for x in [8.5e-8, 16.635532]).
-__device__ __forceinline__ float phi_dev(float x) { return sb_phif(x); }
+// Message invariant of this kernel: a v2c message is never -0.0f. The initial v2c is canonicalised (llr + 0.0f) and
+// the VN update clip(x_tot - c2v) cannot yield -0.0f because x_tot = (0 + sum c2v) + llr is never -0.0f. Hence in the
+// CN phase  sign bit set <=> v2c < 0, which is the reference's sign() with sign(0) := +1 (decoding.py:800-804, :1129).
+// (c2v messages may be -0.0f; the VN arithmetic does not depend on the sign of a zero.)
 
 // ---- check-node updates on the edges pm[0], pm[Z], pm[2Z], ... of one check ------------------------------------
+// boxplus-phi (decoding.py:1126-1166), two edges per step on the packed fp32x2 pipe (sb_math2.cuh)
 __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip) {
     float P = 0.f;
     unsigned par = 0;
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        float* q = pm + l * Z;
-        float v = __fadd_rn(*q, 0.f);                     // -0 -> +0: afterwards sign bit <=> v < 0 (sign(0) := +1)
-        unsigned b = __float_as_uint(v);
-        par ^= b;
-        float p = phi_dev(fabsf(v));                      // >= 0 (tests/test_sb_math.py)
+    int l = 0;
+#pragma unroll 2
+    for (; l + 1 < deg; l += 2) {
+        float* q0 = pm + l * Z;
+        float* q1 = q0 + Z;
+        unsigned b0 = __float_as_uint(*q0), b1 = __float_as_uint(*q1);
+        par ^= b0 ^ b1;
+        float2 p = sb_phif2(make_float2(__uint_as_float(b0 & 0x7fffffffu), __uint_as_float(b1 & 0x7fffffffu)));
+        P = __fadd_rn(P, p.x);                            // :1150 sequential sum, ascending VN
+        P = __fadd_rn(P, p.y);
+        *q0 = __uint_as_float(__float_as_uint(p.x) | (b0 & 0x80000000u));   // phi >= 0: sign bit carries sign(x)
+        *q1 = __uint_as_float(__float_as_uint(p.y) | (b1 & 0x80000000u));
+    }
+    if (l < deg) {
+        float* q0 = pm + l * Z;
+        unsigned b0 = __float_as_uint(*q0);
+        par ^= b0;
+        float p = sb_phif(__uint_as_float(b0 & 0x7fffffffu));
         P = __fadd_rn(P, p);
-        *q = __uint_as_float(__float_as_uint(p) | (b & 0x80000000u));
+        *q0 = __uint_as_float(__float_as_uint(p) | (b0 & 0x80000000u));
     }
     par &= 0x80000000u;
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        float* q = pm + l * Z;
-        unsigned b = __float_as_uint(*q);
-        float p = __uint_as_float(b & 0x7fffffffu);
-        float y = fminf(phi_dev(__fadd_rn(-p, P)), clip); // clip(s*y) == s*min(y, clip) for y >= 0
-        *q = __uint_as_float(__float_as_uint(y) | ((b ^ par) & 0x80000000u));
+    l = 0;
+#pragma unroll 2
+    for (; l + 1 < deg; l += 2) {
+        float* q0 = pm + l * Z;
+        float* q1 = q0 + Z;
+        unsigned b0 = __float_as_uint(*q0), b1 = __float_as_uint(*q1);
+        float2 m = __fadd2_rn(make_float2(__uint_as_float(b0 | 0x80000000u), __uint_as_float(b1 | 0x80000000u)),
+                              make_float2(P, P));         // (-p) + P  (:1155)
+        float2 y = sb_phif2(m);
+        *q0 = __uint_as_float(__float_as_uint(fminf(y.x, clip)) | ((b0 ^ par) & 0x80000000u));   // :1161-1163
+        *q1 = __uint_as_float(__float_as_uint(fminf(y.y, clip)) | ((b1 ^ par) & 0x80000000u));
+    }
+    if (l < deg) {
+        float* q0 = pm + l * Z;
+        unsigned b0 = __float_as_uint(*q0);
+        float y = sb_phif(__fadd_rn(__uint_as_float(b0 | 0x80000000u), P));
+        *q0 = __uint_as_float(__float_as_uint(fminf(y, clip)) | ((b0 ^ par) & 0x80000000u));
     }
 }
 
@@ -101,9 +132,8 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
     unsigned par = 0;
 #pragma unroll
     for (int l = 0; l < DMAX; ++l) {
-        const bool on = l < deg;                          // warp-uniform
         float v = INFINITY;                               // neutral: never the minimum, sign +
-        if (on) v = __fadd_rn(pm[l * Z], 0.f);
+        if (l < deg) v = pm[l * Z];                       // warp-uniform predicate
         x[l] = v;
         float a = fabsf(v);
         m2 = fminf(m2, fmaxf(m1, a));
@@ -129,7 +159,7 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
     float m1 = INFINITY, m2 = INFINITY;
     unsigned par = 0;
     for (int l = 0; l < deg; ++l) {
-        float v = __fadd_rn(pm[l * Z], 0.f);
+        float v = pm[l * Z];
         float a = fabsf(v);
         m2 = fminf(m2, fmaxf(m1, a));
         m1 = fminf(m1, a);
@@ -141,135 +171,224 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
     const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
     const float oe = fminf(fmaxf(__fsub_rn(min_e, offset), 0.f), clip);
     for (int l = 0; l < deg; ++l) {
-        float v = __fadd_rn(pm[l * Z], 0.f);
+        float v = pm[l * Z];
         float mag = (fabsf(v) == m1) ? oe : o1;
         pm[l * Z] = __uint_as_float(__float_as_uint(mag) | ((__float_as_uint(v) ^ par) & 0x80000000u));
     }
 }
 
-template <int RULE>
+template <int RULE, int CLS>
 __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset) {
     if (RULE == SB_CN_BOXPLUS_PHI) cn_phi_qc(pm, Z, deg, clip);
     else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
         const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
-        if (deg <= 4) cn_minsum_qc<4>(pm, Z, deg, clip, off);
-        else if (deg <= 8) cn_minsum_qc<8>(pm, Z, deg, clip, off);
-        else if (deg <= 12) cn_minsum_qc<12>(pm, Z, deg, clip, off);
-        else if (deg <= 20) cn_minsum_qc<20>(pm, Z, deg, clip, off);
+        if (CLS == 4) cn_minsum_qc<4>(pm, Z, deg, clip, off);
+        else if (CLS == 3) cn_minsum_qc<8>(pm, Z, deg, clip, off);
+        else if (CLS == 2) cn_minsum_qc<12>(pm, Z, deg, clip, off);
+        else if (CLS == 1) cn_minsum_qc<20>(pm, Z, deg, clip, off);
         else cn_minsum_qc_loop(pm, Z, deg, clip, off);
     }
 }
 
-// ---- variable-node update (decoding.py:714-732) for VN (c, j); msgb = message array as bytes -----------------
+// explicit shared-window accesses with 32-bit addresses (no generic-address arithmetic in the hot loops)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+// ---- variable-node update (decoding.py:714-732) for VN (c, j) -------------------------------------------------
+// msg_s / ce_s are 32-bit shared-window addresses of the message array and of the column's first table entry.
 // Returns the unclipped x_tot. MODE 0: normal update; MODE 1: initialisation v2c = llr (decoding.py:571).
+// Branch free: table entries beyond the column's degree are not read (predicate), their slot address points at the
+// VN's own first edge and the accumulate / store are predicated off.
 template <int DMAX, bool CHECK, bool KEEPM, int MODE>
-__device__ __forceinline__ float vn_qc(char* msgb, const int2* ce, int deg, int j4, int Z4, float llr, float clip) {
-    int addr[DMAX];                                       // assigned unconditionally so the arrays stay in registers
+__device__ __forceinline__ float vn_qc(uint32_t msg_s, uint32_t ce_s, int deg, int j4, int Z4, float llr, float clip) {
+    uint32_t addr[DMAX];
     float m[KEEPM ? DMAX : 1];
+    bool on[DMAX];
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) {
-        int a = -1;
+        int2 e = make_int2(0, 0);
+        if (k < deg) e = lds_i2(ce_s + 8 * k);            // warp-uniform predicate
+        int t = j4 - (e.y & 0xffff);
+        t += (t >> 31) & Z4;                              // (j - s) mod Z, in bytes
+        bool ok = (k < deg) && (!CHECK || t < (int)((unsigned)e.y >> 16));   // edge exists
+        on[k] = ok;
+        addr[k] = msg_s + e.x + t;
         float v = 0.f;
-        if (k < deg) {                                    // warp-uniform
-            int2 e = ce[k];
-            int t = j4 - (e.y & 0xffff);
-            t += (t >> 31) & Z4;                          // (j - s) mod Z, in bytes
-            bool ok = !CHECK || t < (int)((unsigned)e.y >> 16);   // edge exists (row not cut by pruning)
-            if (ok) {
-                a = e.x + t;
-                if (MODE == 0) {
-                    v = *reinterpret_cast<float*>(msgb + a);
-                    acc = __fadd_rn(acc, v);              // :715 sequential, ascending CN
-                }
-            }
+        if (MODE == 0) {
+            if (ok) v = lds_f32(addr[k]);
+            if (ok) acc = __fadd_rn(acc, v);              // :715 sequential, ascending CN
         }
-        addr[k] = a;
-        if (KEEPM) m[k] = v;
+        if (KEEPM) m[KEEPM ? k : 0] = v;
     }
     float x_tot = __fadd_rn(acc, llr);                    // :716
+    const float init = __fadd_rn(llr, 0.f);               // canonical +0.0 for punctured bits (llr = -0.0)
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) {
-        int a = addr[k];
-        if (k < deg && (!CHECK || a >= 0)) {
-            float* q = reinterpret_cast<float*>(msgb + a);
-            if (MODE == 1) *q = llr;
-            else {
-                float v = KEEPM ? m[KEEPM ? k : 0] : *q;
-                *q = clipf(__fadd_rn(-v, x_tot), clip);    // :724-729
-            }
+        if (MODE == 1) {
+            if (on[k]) sts_f32(addr[k], init);
+        } else {
+            float v = 0.f;
+            if (KEEPM) v = m[KEEPM ? k : 0];
+            else if (on[k]) v = lds_f32(addr[k]);
+            float y = clipf(__fadd_rn(-v, x_tot), clip);  // :724-729
+            if (on[k]) sts_f32(addr[k], y);
         }
     }
     return x_tot;
 }
 
 template <int MODE>
-__device__ __forceinline__ float vn_qc_loop(char* msgb, const int2* ce, int deg, int j4, int Z4, float llr, float clip) {
+__device__ __forceinline__ float vn_qc_loop(uint32_t msg_s, uint32_t ce_s, int deg, int j4, int Z4, float llr, float clip) {
     float acc = 0.f;
     if (MODE == 0)
         for (int k = 0; k < deg; ++k) {
-            int2 e = ce[k];
+            int2 e = lds_i2(ce_s + 8 * k);
             int t = j4 - (e.y & 0xffff);
             t += (t >> 31) & Z4;
-            if (t < (int)((unsigned)e.y >> 16)) acc = __fadd_rn(acc, *reinterpret_cast<float*>(msgb + e.x + t));
+            if (t < (int)((unsigned)e.y >> 16)) acc = __fadd_rn(acc, lds_f32(msg_s + e.x + t));
         }
     float x_tot = __fadd_rn(acc, llr);
     for (int k = 0; k < deg; ++k) {
-        int2 e = ce[k];
+        int2 e = lds_i2(ce_s + 8 * k);
         int t = j4 - (e.y & 0xffff);
         t += (t >> 31) & Z4;
         if (t < (int)((unsigned)e.y >> 16)) {
-            float* q = reinterpret_cast<float*>(msgb + e.x + t);
-            *q = (MODE == 1) ? llr : clipf(__fadd_rn(-*q, x_tot), clip);
+            uint32_t a = msg_s + e.x + t;
+            sts_f32(a, (MODE == 1) ? __fadd_rn(llr, 0.f) : clipf(__fadd_rn(-lds_f32(a), x_tot), clip));
         }
     }
     return x_tot;
 }
 
-template <int MODE>
-__device__ __forceinline__ float vn_dispatch(char* msgb, const int2* ce, int deg, bool check, int j4, int Z4, float llr,
-                                             float clip) {
-    if (!check) {
-        if (deg <= 2) return vn_qc<2, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 4) return vn_qc<4, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 8) return vn_qc<8, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 12) return vn_qc<12, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 20) return vn_qc<20, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 32) return vn_qc<32, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    } else {
-        if (deg <= 4) return vn_qc<4, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-        if (deg <= 12) return vn_qc<12, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    }
+// VN classes (host: col_class()): 0 loop (deg > 32), 1 <=32, 2 <=20, 3 <=12, 4 <=8, 5 <=4, 6 <=2; with edges into a
+// pruning-cut row: 7 loop, 8 <=12, 9 <=4; 10: degree-1 columns whose update is fused into the CN phase.
+template <int MODE, int CLS>
+__device__ __forceinline__ float vn_cls(uint32_t msgb, uint32_t ce, int deg, int j4, int Z4, float llr, float clip) {
+    if (CLS == 1) return vn_qc<32, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 2) return vn_qc<20, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 3) return vn_qc<12, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 4) return vn_qc<8, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 5) return vn_qc<4, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 6) return vn_qc<2, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 8) return vn_qc<12, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 9) return vn_qc<4, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    if (CLS == 10) return vn_qc<1, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
     return vn_qc_loop<MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+}
+
+struct WarpCtx {
+    int G, grp, lane_i;
+};
+
+// first index >= start that is congruent to grp modulo G (rows/columns are dealt cyclically over ALL classes);
+// start_mod = start mod G comes from the host
+__device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx& w) {
+    return start + (w.grp - start_mod + (w.grp < start_mod ? w.G : 0));
+}
+
+template <int RULE, int CLS>
+__device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
+                                         const int4* s_row, int start, int end, float clip, bool fuse) {
+    for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
+        int4 ri = s_row[rr];
+        if (w.lane_i < ri.z) {
+            float* pm = msg + ri.x * p.Z + w.lane_i;
+            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset);
+            if (fuse && ri.w >= 0) {
+                // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
+                // with a single incoming message) so the VN phase can skip the column
+                int s = ri.w >> 16, vb = ri.w & 0xffff;     // shift, column index
+                int j = w.lane_i + s;
+                j -= (j >= p.Z) ? p.Z : 0;
+                float* q = pm + (ri.y - 1) * p.Z;
+                float c2v = *q;
+                float x_tot = __fadd_rn(__fadd_rn(0.f, c2v), llr_s[vb * p.Z + j]);
+                *q = clipf(__fadd_rn(-c2v, x_tot), clip);
+            }
+        }
+    }
+}
+
+template <int MODE, int CLS>
+__device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
+                                         const int4* s_col, uint32_t s_ce, int start, int end, float clip,
+                                         bool final_pass, long long b) {
+    for (int cc = first_of(start, p.col_cls_mod[CLS], w); cc < end; cc += w.G) {
+        int4 ci = s_col[cc];
+        if (w.lane_i < ci.z) {
+            int v = ci.w + w.lane_i;
+            float x_tot = vn_cls<MODE, CLS>(msgb, s_ce + 8 * ci.x, ci.y, 4 * w.lane_i, 4 * p.Z, llr_s[v], clip);
+            if (MODE == 0 && final_pass) {
+                int o = p.out_pos[v];
+                if (o >= 0) {
+                    x_tot = clipf(x_tot, clip);                                              // :730
+                    p.out[(size_t)b * p.n_out + o] = p.hard_out ? (0.f >= x_tot ? 1.f : 0.f) // :622-626
+                                                                : __fmul_rn(x_tot, -1.f);
+                }
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
+                                       const int4* s_col, uint32_t s_ce, float clip, bool final_pass,
+                                       bool with_fused, long long b) {
+    const int* ce = p.col_cls_end;
+    vn_class<MODE, 0>(p, w, msgb, llr_s, s_col, s_ce, 0, ce[0], clip, final_pass, b);
+    vn_class<MODE, 1>(p, w, msgb, llr_s, s_col, s_ce, ce[0], ce[1], clip, final_pass, b);
+    vn_class<MODE, 2>(p, w, msgb, llr_s, s_col, s_ce, ce[1], ce[2], clip, final_pass, b);
+    vn_class<MODE, 3>(p, w, msgb, llr_s, s_col, s_ce, ce[2], ce[3], clip, final_pass, b);
+    vn_class<MODE, 4>(p, w, msgb, llr_s, s_col, s_ce, ce[3], ce[4], clip, final_pass, b);
+    vn_class<MODE, 5>(p, w, msgb, llr_s, s_col, s_ce, ce[4], ce[5], clip, final_pass, b);
+    vn_class<MODE, 6>(p, w, msgb, llr_s, s_col, s_ce, ce[5], ce[6], clip, final_pass, b);
+    vn_class<MODE, 7>(p, w, msgb, llr_s, s_col, s_ce, ce[6], ce[7], clip, final_pass, b);
+    vn_class<MODE, 8>(p, w, msgb, llr_s, s_col, s_ce, ce[7], ce[8], clip, final_pass, b);
+    vn_class<MODE, 9>(p, w, msgb, llr_s, s_col, s_ce, ce[8], ce[9], clip, final_pass, b);
+    if (with_fused) vn_class<MODE, 10>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
 }
 
 template <int RULE>
 __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
-    const int Z = p.Z, Z4 = 4 * Z, N = p.N, Zb = (Z + 31) >> 5;
+    const int Z = p.Z, N = p.N, Zb = (Z + 31) >> 5;
     // carve-up by byte offsets from the __shared__ base (keeps the shared address space visible to the compiler)
     const int off_llr = p.E_alloc * 4;
     const int off_col = (off_llr + N * 4 + 15) & ~15;
     const int off_row = off_col + p.n_cols * 16;
-    const int off_ce = off_row + p.n_rows * 8;
+    const int off_ce = off_row + p.n_rows * 16;
     const int off_bar = (off_ce + p.nnz * 8 + 15) & ~15;
     float* msg = reinterpret_cast<float*>(smem_raw);
     float* llr_s = reinterpret_cast<float*>(smem_raw + off_llr);
     int4* s_col = reinterpret_cast<int4*>(smem_raw + off_col);
-    int2* s_row = reinterpret_cast<int2*>(smem_raw + off_row);
-    int2* s_ce = reinterpret_cast<int2*>(smem_raw + off_ce);
+    int4* s_row = reinterpret_cast<int4*>(smem_raw + off_row);
+    int2* s_ce_p = reinterpret_cast<int2*>(smem_raw + off_ce);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
-    char* msgb = reinterpret_cast<char*>(smem_raw);
+    const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
+    const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
-    const int G = W / Zb, grp = warp / Zb, ib = warp - grp * Zb;
-    const bool warp_used = warp < G * Zb;
-    const int lane_i = ib * 32 + lane;
+    WarpCtx w;
+    w.G = W / Zb;
+    w.grp = warp / Zb;
+    w.lane_i = (warp - w.grp * Zb) * 32 + lane;
 
     for (int i = tid; i < p.n_cols; i += T) s_col[i] = p.col_info[i];
     for (int i = tid; i < p.n_rows; i += T) s_row[i] = p.row_info[i];
-    for (int i = tid; i < p.nnz; i += T) s_ce[i] = p.col_edge[i];
+    for (int i = tid; i < p.nnz; i += T) s_ce_p[i] = p.col_edge[i];
     if (p.use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -304,13 +423,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
         }
         __syncthreads();
         // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
-        if (warp_used)
-            for (int cc = grp; cc < p.n_cols; cc += G) {
-                int4 ci = s_col[cc];
-                if (lane_i < ci.z)
-                    vn_dispatch<1>(msgb, s_ce + ci.x, ci.y & 0xffff, (ci.y >> 16) != 0, 4 * lane_i, Z4,
-                                   llr_s[ci.w + lane_i], clip);
-            }
+        vn_all<1>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
         __syncthreads();
         if (p.num_iter == 0) {
             for (int v = tid; v < N; v += T) {
@@ -322,32 +435,17 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
             }
         }
         for (int it = 0; it < p.num_iter; ++it) {
-            // ---- CN phase ---------------------------------------------------------------------------------------
-            if (warp_used)
-                for (int rr = grp; rr < p.n_rows; rr += G) {
-                    int2 ri = s_row[rr];
-                    if (lane_i < (ri.y >> 16)) cn_qc<RULE>(msg + ri.x * Z + lane_i, Z, ri.y & 0xffff, clip, p.offset);
-                }
+            const bool final_pass = it == p.num_iter - 1;
+            // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
+            const int* re = p.row_cls_end;
+            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass);
+            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass);
+            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass);
+            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass);
+            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass);
             __syncthreads();
             // ---- VN phase ---------------------------------------------------------------------------------------
-            const bool final_pass = it == p.num_iter - 1;
-            if (warp_used)
-            for (int cc = grp; cc < p.n_cols; cc += G) {
-                int4 ci = s_col[cc];
-                if (lane_i < ci.z) {
-                    int v = ci.w + lane_i;
-                    float x_tot = vn_dispatch<0>(msgb, s_ce + ci.x, ci.y & 0xffff, (ci.y >> 16) != 0, 4 * lane_i, Z4,
-                                                 llr_s[v], clip);
-                    if (final_pass) {
-                        int o = p.out_pos[v];
-                        if (o >= 0) {
-                            x_tot = clipf(x_tot, clip);                                              // :730
-                            p.out[(size_t)b * p.n_out + o] = p.hard_out ? (0.f >= x_tot ? 1.f : 0.f) // :622-626
-                                                                        : __fmul_rn(x_tot, -1.f);
-                        }
-                    }
-                }
-            }
+            vn_all<0>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
             __syncthreads();
         }
         if (p.state_out) {
@@ -359,7 +457,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
 }
 
 size_t qc_smem_bytes(const sb_ldpc_graph* g) {
-    return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 8 +
+    return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 16 +
            (size_t)g->qc_nnz * 8 + 16 + 16;
 }
 
@@ -439,25 +537,53 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
             ++total;
         }
     if (total != E) { sb_set_error("sb_ldpc_graph_set_qc: %lld lifted edges != %d graph edges", total, E); return SB_EINVAL; }
-    // rows / columns by decreasing degree (stable)
+    // classes (see the kernel): rows by degree bucket, heaviest first; columns by bucket / pruning-cut rows / fused
     std::vector<int> rdeg(n_rows, 0), cdeg(n_cols, 0);
     for (const Ent& en : ents) { ++rdeg[en.r]; ++cdeg[en.c]; }
+    std::vector<std::vector<Ent>> by_row(n_rows), by_col(n_cols);
+    for (const Ent& en : ents) { by_row[en.r].push_back(en); by_col[en.c].push_back(en); }
+    for (auto& v : by_row) std::sort(v.begin(), v.end(), [](const Ent& a, const Ent& b) { return a.c < b.c; });
+    for (auto& v : by_col) std::sort(v.begin(), v.end(), [](const Ent& a, const Ent& b) { return a.r < b.r; });
+    // a degree-1 column whose single entry is the LAST entry of its row is updated inside the CN phase
+    std::vector<int> fused_col_of_row(n_rows, -1);
+    std::vector<char> col_fused(n_cols, 0);
+    for (int r = 0; r < n_rows; ++r) {
+        if (by_row[r].empty()) continue;
+        const Ent& last = by_row[r].back();
+        if (cdeg[last.c] == 1 && rdeg[r] >= 2 && last.c < 65536 && zcol(last.c) == zrow(r)) {
+            fused_col_of_row[r] = last.c;
+            col_fused[last.c] = 1;
+        }
+    }
+    auto row_class = [&](int r) { int d = rdeg[r]; return d > 20 ? 0 : d > 12 ? 1 : d > 8 ? 2 : d > 4 ? 3 : 4; };
+    auto col_class = [&](int c) {
+        if (col_fused[c]) return 10;
+        bool check = false;
+        for (const Ent& en : by_col[c]) check = check || zrow(en.r) < Z;
+        int d = cdeg[c];
+        if (check) return d > 12 ? 7 : d > 4 ? 8 : 9;
+        return d > 32 ? 0 : d > 20 ? 1 : d > 12 ? 2 : d > 8 ? 3 : d > 4 ? 4 : d > 2 ? 5 : 6;
+    };
     std::vector<int> rorder(n_rows), corder(n_cols);
     std::iota(rorder.begin(), rorder.end(), 0);
     std::iota(corder.begin(), corder.end(), 0);
-    std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) { return rdeg[a] > rdeg[b]; });
-    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cdeg[a] > cdeg[b]; });
+    std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) {
+        return row_class(a) != row_class(b) ? row_class(a) < row_class(b) : rdeg[a] > rdeg[b]; });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) {
+        return col_class(a) != col_class(b) ? col_class(a) < col_class(b) : cdeg[a] > cdeg[b]; });
+    std::vector<int> row_cls_end(5, 0), col_cls_end(11, 0);
+    for (int r = 0; r < n_rows; ++r) for (int k = row_class(r); k < 5; ++k) ++row_cls_end[k];
+    for (int c = 0; c < n_cols; ++c) for (int k = col_class(c); k < 11; ++k) ++col_cls_end[k];
     // base-entry numbering: rows in processing order, ascending column inside a row
     std::vector<int> be_of((size_t)n_rows * n_cols, -1);
-    std::vector<int> row_info(2 * n_rows), shift_of(ents.size());
-    std::vector<std::vector<Ent>> by_row(n_rows), by_col(n_cols);
-    for (const Ent& en : ents) { by_row[en.r].push_back(en); by_col[en.c].push_back(en); }
+    std::vector<int> row_info(4 * n_rows);
     int be = 0;
     for (int rr = 0; rr < n_rows; ++rr) {
         int r = rorder[rr];
-        std::sort(by_row[r].begin(), by_row[r].end(), [](const Ent& a, const Ent& b) { return a.c < b.c; });
-        row_info[2 * rr] = be;
-        row_info[2 * rr + 1] = rdeg[r] | (zrow(r) << 16);
+        row_info[4 * rr] = be;
+        row_info[4 * rr + 1] = rdeg[r];
+        row_info[4 * rr + 2] = zrow(r);
+        row_info[4 * rr + 3] = fused_col_of_row[r] >= 0 ? (fused_col_of_row[r] | (by_row[r].back().s << 16)) : -1;
         for (const Ent& en : by_row[r]) {
             if (be_of[(size_t)en.r * n_cols + en.c] != -1) { sb_set_error("sb_ldpc_graph_set_qc: duplicate base entry"); return SB_EINVAL; }
             be_of[(size_t)en.r * n_cols + en.c] = be++;
@@ -468,16 +594,13 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
     int ce = 0;
     for (int cc = 0; cc < n_cols; ++cc) {
         int c = corder[cc];
-        std::sort(by_col[c].begin(), by_col[c].end(), [](const Ent& a, const Ent& b) { return a.r < b.r; });
-        bool check = false;
         col_info[4 * cc] = ce;
         for (const Ent& en : by_col[c]) {
             col_edge[2 * ce] = be_of[(size_t)en.r * n_cols + en.c] * Z * 4;
             col_edge[2 * ce + 1] = (en.s * 4) | ((zrow(en.r) * 4) << 16);
-            check = check || zrow(en.r) < Z;
             ++ce;
         }
-        col_info[4 * cc + 1] = cdeg[c] | ((check ? 1 : 0) << 16);
+        col_info[4 * cc + 1] = cdeg[c];
         col_info[4 * cc + 2] = zcol(c);
         col_info[4 * cc + 3] = c * Z;
     }
@@ -493,7 +616,27 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
     g->qc_max_row_deg = *std::max_element(rdeg.begin(), rdeg.end());
     g->qc_max_col_deg = *std::max_element(cdeg.begin(), cdeg.end());
     g->qc_row_info.swap(row_info); g->qc_col_info.swap(col_info); g->qc_col_edge.swap(col_edge);
+    g->qc_row_cls_end = row_cls_end; g->qc_col_cls_end = col_cls_end;
     g->qc_in_idx.swap(in_nat); g->qc_out_pos.swap(out_nat); g->qc_slot_of_edge.swap(slot);
+    return SB_OK;
+}
+
+// Test hook: evaluates phi on the device with the scalar (sb_math.h) and the packed (sb_math2.cuh) implementation.
+namespace {
+__global__ void debug_phi_kernel(const float* x, float* o1, float* o2, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * i + 1 < n) {
+        float2 r = sb_phif2(make_float2(x[2 * i], x[2 * i + 1]));
+        o2[2 * i] = r.x; o2[2 * i + 1] = r.y;
+        o1[2 * i] = sb_phif(x[2 * i]); o1[2 * i + 1] = sb_phif(x[2 * i + 1]);
+    }
+}
+}  // namespace
+extern "C" int sb_debug_phi(const float* d_x, float* d_scalar, float* d_packed, int64_t n, void* stream) {
+    SB_CHECK_ARG(d_x && d_scalar && d_packed && n >= 0 && n % 2 == 0, "sb_debug_phi: bad arguments");
+    if (n == 0) return SB_OK;
+    debug_phi_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_scalar, d_packed, n);
+    SB_LAUNCH_CHECK();
     return SB_OK;
 }
 
@@ -514,7 +657,9 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     QcParams p{};
     p.Z = g->qc_Z; p.n_rows = g->qc_rows; p.n_cols = g->qc_cols; p.nnz = g->qc_nnz; p.N = g->N; p.E = g->E;
     p.E_alloc = g->qc_nnz * g->qc_Z; p.n_in = g->n_in; p.n_out = g->n_out;
-    p.row_info = (const int2*)g->d_qc_row_info; p.col_info = (const int4*)g->d_qc_col_info;
+    for (int k = 0; k < kRowClasses; ++k) p.row_cls_end[k] = g->qc_row_cls_end[k];
+    for (int k = 0; k < kColClasses; ++k) p.col_cls_end[k] = g->qc_col_cls_end[k];
+    p.row_info = (const int4*)g->d_qc_row_info; p.col_info = (const int4*)g->d_qc_col_info;
     p.col_edge = (const int2*)g->d_qc_col_edge; p.in_idx = g->d_qc_in_idx; p.out_pos = g->d_qc_out_pos;
     p.slot_of_edge = g->d_qc_slot_of_edge;
     p.llr = d_llr; p.out = d_out; p.state_out = d_state_out; p.B = batch; p.num_iter = num_iter; p.hard_out = hard_out;
@@ -523,6 +668,8 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
     int groups = std::max(1, std::min(24 / Zb, std::max(g->qc_rows, g->qc_cols)));
     const int threads = groups * Zb * 32;                  // every warp owns one slice index for the whole launch
+    for (int k = 0; k < kRowClasses; ++k) p.row_cls_mod[k] = (k ? g->qc_row_cls_end[k - 1] : 0) % groups;
+    for (int k = 0; k < kColClasses; ++k) p.col_cls_mod[k] = (k ? g->qc_col_cls_end[k - 1] : 0) % groups;
     switch (cn_rule) {
         case SB_CN_BOXPLUS_PHI: rc = launch_qc<SB_CN_BOXPLUS_PHI>(g, p, threads, smem, stream); break;
         case SB_CN_BOXPLUS: rc = launch_qc<SB_CN_BOXPLUS>(g, p, threads, smem, stream); break;

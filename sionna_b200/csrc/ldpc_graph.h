@@ -22,11 +22,11 @@ struct sb_ldpc_graph {
     // ---- quasi-cyclic description (optional, set by sb_ldpc_graph_set_qc; used by ldpc_bp_qc.cu) ----------
     bool qc = false;
     int qc_Z = 0, qc_rows = 0, qc_cols = 0, qc_nnz = 0, qc_max_row_deg = 0, qc_max_col_deg = 0;
-    std::vector<int> qc_row_info;   // int2 per base row (processing order): {first base entry, deg | zrow << 16}
+    std::vector<int> qc_row_info;   // int4 per base row (processing order): {first base entry, deg, zrow, fused col | s << 16 or -1}
     std::vector<int> qc_col_info;   // int4 per base col (processing order): {first col-edge, deg, zcol, c*Z}
     std::vector<int> qc_col_edge;   // int2 per (col, entry), ascending base row: {be*Z*4, s*4 | (zrow*4) << 16}
     std::vector<int> qc_in_idx, qc_out_pos, qc_slot_of_edge;   // natural VN order / reference edge order
-    std::vector<char> qc_col_check; // per base col (processing order): 1 if any entry lies in a partial row
+    std::vector<int> qc_row_cls_end, qc_col_cls_end;   // class boundaries in processing order (ldpc_bp_qc.cu)
     int *d_qc_row_info = nullptr, *d_qc_col_info = nullptr, *d_qc_col_edge = nullptr, *d_qc_in_idx = nullptr,
         *d_qc_out_pos = nullptr, *d_qc_slot_of_edge = nullptr;
     bool qc_uploaded = false;

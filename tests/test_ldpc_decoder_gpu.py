@@ -191,3 +191,18 @@ def test_qc_zero_iterations_and_large_llr_max(cuda_device):
         ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=False, num_iter=3, llr_max=90000.0)
         assert np.array_equal(dec(torch.from_numpy(big).to(cuda_device)).cpu().numpy(),
                               ref(big, math_mode=1, order="kernel"))
+
+
+def test_device_phi_scalar_and_packed_equal_oracle(cuda_device):
+    """phi() on the device (scalar sb_math.h path and packed FFMA2 path of sb_math2.cuh) == CPU oracle, bit for bit."""
+    import ctypes
+    from sionna_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 20, 200000), 10 ** rng.uniform(-9, 1.3, 200000), [0, 8.5e-8, 16.635532, 40, 1, 10]])
+    x = x.astype(np.float32)[: (len(x) // 2) * 2]
+    xd = torch.from_numpy(x).to(cuda_device)
+    o1, o2 = torch.empty_like(xd), torch.empty_like(xd)
+    _lib.check(_lib.lib().sb_debug_phi(_lib.ptr(xd), _lib.ptr(o1), _lib.ptr(o2), len(x), _lib.current_stream()), "sb_debug_phi")
+    ref = np.array([O.phi(v, 1) for v in x[:5000]], np.float32)
+    assert np.array_equal(o1.cpu().numpy()[:5000], ref)
+    assert torch.equal(o1, o2)
