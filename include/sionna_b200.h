@@ -150,6 +150,64 @@ int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, i
  * d_counters[0] += #(b != b_hat); [1] += #rows with any difference; [2] += rows*k; [3] += rows  (int64[4], device). */
 int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_t k, int64_t* d_counters, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * OFDM, resource grid, channel estimation, MIMO equalisation (complex64 = interleaved float pairs)
+ * ---------------------------------------------------------------------------------------------- */
+/* OFDMModulator.call (ofdm/modulator.py:97-124): d_x [rows, num_symbols, fft_size] frequency-domain grid (DC centred)
+ * -> d_out [rows, out_len]; symbol l starts at d_out_off[l] and carries d_cp[l] cyclic-prefix samples:
+ * ifftshift, ifft * sqrt(N) (signal/utils.py:206-249), CP = last cp samples prepended. Any fft_size <= 8192. */
+int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
+                     const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, void* stream);
+/* OFDMDemodulator.call (ofdm/demodulator.py:162-203): d_x [rows, in_len] time samples -> d_out [rows, num_symbols,
+ * fft_size]: CP removal, fft / sqrt(N), phase compensation exp(-j 2 pi k l_min / N), fftshift. */
+int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
+                       const int32_t* d_cp, const int32_t* d_in_off, int32_t in_len, int32_t l_min, void* stream);
+/* out[b, r, j] = in[b, (in_rows == 1 ? 0 : r), idx[r, j]] (0 where idx < 0); words = 1 (fp32) or 2 (complex64).
+ * Replaces the tf.gather re-indexing of RemoveNulledSubcarriers (ofdm/resource_grid.py:551), ResourceGridDemapper
+ * (:466-520) and NearestNeighborInterpolator (ofdm/channel_estimation.py:409-435). */
+int sb_gather_rows(const float* d_in, const int32_t* d_idx, float* d_out, int64_t batch, int32_t rows, int32_t cols_out,
+                   int32_t in_rows, int32_t cols_in, int32_t words, void* stream);
+/* ResourceGridMapper.call (ofdm/resource_grid.py:394-412): d_x [batch, num_streams, num_data], d_pilots [num_streams,
+ * num_pilots], d_map [num_streams, grid_size] (>= 0 data index, -1 empty, <= -2 pilot index -(v+2)) -> d_out
+ * [batch, num_streams, grid_size]. */
+int sb_rg_map(const float* d_x, const float* d_pilots, const int32_t* d_map, float* d_out, int64_t batch,
+              int32_t num_streams, int32_t grid_size, int32_t num_data, int32_t num_pilots, void* stream);
+/* Pilot gather (ofdm/channel_estimation.py:138-150) + LSChannelEstimator.estimate_at_pilot_locations (:257-285):
+ * d_y [batch, grid_size] (effective subcarriers, flattened), d_pilot_ind / d_pilots [num_streams, num_pilots], d_no
+ * [batch / no_inner] -> d_h [batch, num_streams, num_pilots] = y / p, d_err = no / |p|^2 (both 0 where p == 0). */
+int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, const float* d_pilots, const float* d_no,
+                    int64_t no_inner, float* d_h, float* d_err, int64_t batch, int32_t num_streams, int32_t num_pilots,
+                    int32_t grid_size, void* stream);
+/* LinearInterpolator._interpolate (ofdm/channel_estimation.py:657-734) with the index tables of :522-655:
+ * d_h [batch, num_streams, num_pilots] -> d_out [batch, num_streams, num_symbols, num_subcarriers]. */
+int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, const int32_t* d_fy0,
+                  const int32_t* d_fy1, const int32_t* d_ty0, const int32_t* d_ty1, const int32_t* d_npil,
+                  int32_t time_avg, float* d_out, int64_t batch, int32_t num_streams, int32_t num_symbols,
+                  int32_t num_subcarriers, int32_t num_pilots, void* stream);
+/* ApplyOFDMChannel.call (channel/apply_ofdm_channel.py:70-80): y[b, r, re] = sum_t h[b, r, t, re] x[b, t, re] + w,
+ * r over rx antennas, t over tx antennas, w ~ CN(0, no) if add_noise. */
+int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
+                          int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_re,
+                          int32_t add_noise, uint64_t seed, uint64_t offset, void* stream);
+/* lmmse_equalizer (mimo/equalization.py:101-233, whiten_interference=True): d_y [num, M], d_h [num, M, K], d_s [num, M, M]
+ * -> d_x_hat [num, K] complex, d_no_eff [num, K] real. 1 <= K <= 16, K <= M. */
+int sb_lmmse_equalize(const float* d_y, const float* d_h, const float* d_s, float* d_x_hat, float* d_no_eff, int64_t num,
+                      int32_t M, int32_t K, void* stream);
+/* OFDMEqualizer.call with the LMMSE equaliser fused in (ofdm/equalization.py:109-275 + mimo/equalization.py:101-233):
+ * d_y [batch, num_rx, num_rx_ant, num_symbols, num_subcarriers] (effective subcarriers), d_h_hat [batch, num_rx,
+ * num_rx_ant, num_tx_streams, num_symbols, num_subcarriers], d_err_var addressed with h_ev_stride[6] (elements; 0 =
+ * broadcast) over (batch, rx, ant, tx_stream, symbol, subcarrier), d_no with h_no_stride[3] over (batch, rx, ant);
+ * d_desired [num_rx, streams_per_rx] / d_undesired [num_rx, interferers_per_rx]: tx-stream indices per receiver
+ * (mimo/stream_management.py:200-246); d_out_stream [num_rx, streams_per_rx]: output stream row after the stream_ind
+ * re-ordering; d_data_pos [num_tx_streams, num_symbols*num_subcarriers]: index among that stream's data symbols or -1.
+ * Outputs d_x_hat / d_no_eff [batch, num_tx_streams, num_data]. */
+int sb_ofdm_lmmse(const float* d_y, const float* d_h_hat, const float* d_err_var, const int64_t* h_ev_stride,
+                  const float* d_no, const int64_t* h_no_stride, const int32_t* d_desired, const int32_t* d_undesired,
+                  const int32_t* d_out_stream, const int32_t* d_data_pos, float* d_x_hat, float* d_no_eff, int64_t batch,
+                  int32_t num_rx, int32_t num_rx_ant, int32_t num_tx_streams, int32_t num_symbols,
+                  int32_t num_subcarriers, int32_t streams_per_rx, int32_t interferers_per_rx, int32_t num_data,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,3 +5,5 @@ from . import utils
 from . import mapping
 from . import channel
 from . import fec
+from . import mimo
+from . import ofdm

@@ -1,2 +1,3 @@
-"""Channel models on the hot path (mirror of sionna.phy.channel): AWGN."""
+"""Channel models on the hot path (mirror of sionna.phy.channel): AWGN, frequency-domain channel application."""
 from .awgn import AWGN
+from .apply_ofdm_channel import ApplyOFDMChannel

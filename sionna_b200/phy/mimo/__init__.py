@@ -1,0 +1,4 @@
+"""MIMO (mirror of sionna.phy.mimo for the hot path): stream management, LMMSE equalisation, linear detection."""
+from .stream_management import StreamManagement
+from .equalization import lmmse_equalizer
+from .detection import LinearDetector

