@@ -29,3 +29,16 @@ np.savez_compressed(os.path.join(dst, "bg_tables.npz"), **out)
 pcms = np.load(os.path.join(src, "example_codes.npy"), allow_pickle=True)
 np.savez_compressed(os.path.join(dst, "example_pcms.npz"), **{f"pcm{i}": np.array(p, np.uint8) for i, p in enumerate(pcms)})
 for i, p in enumerate(pcms): print("pcm", i, np.array(p).shape)
+
+# ---- TR 38.901 Table 7.7.2-1..5 TDL power delay profiles (normalised delays, powers in dB) --------------------------
+import json
+tdl = {}
+mdir = "/root/reference/src/sionna/phy/channel/tr38901/models"
+for m in "ABCDE":
+    with open(os.path.join(mdir, f"TDL-{m}.json")) as f:
+        d = json.load(f)
+    tdl[f"{m}_delays"] = np.array(d["delays"], np.float64)
+    tdl[f"{m}_powers_db"] = np.array(d["powers"], np.float64)
+    tdl[f"{m}_los"] = np.array(int(d["los"]))
+    print("TDL-" + m, d["num_clusters"], "taps, los", d["los"])
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "..", "sionna_b200", "phy", "channel", "tdl_models.npz"), **tdl)
