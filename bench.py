@@ -144,37 +144,44 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "--gpus must match the torchrun world size"
 
+    from sionna_b200.phy import config as sb_config
+    from sionna_b200.phy.mapping import BinarySource, Mapper, Demapper
+    from sionna_b200.phy.channel import AWGN
+    from sionna_b200.phy.utils import ebnodb2no, ErrorCounter
+
     enc = LDPC5GEncoder(K_INFO, N_CODE)
     dec = LDPC5GDecoder(enc, cn_update=args.cn_update, num_iter=NUM_ITER, hard_out=True, return_infobits=True)
     assert dec.on_chip and dec.num_edges == E_EDGES and dec.num_vns == N_VNS
 
-    # two distinct input sets (2 x 138 MB > 126 MB L2), alternated between steps: nothing the kernel reads from
-    # HBM can be an L2 hit left over from the previous step
-    h_in = [torch.from_numpy(make_inputs(100 + 1000 * rank + i, BATCH)).pin_memory() for i in range(2)]
-    d_in = [h.to(dev) for h in h_in]
-    counters = torch.zeros(4, dtype=torch.int64, device=dev)     # bit errors, block errors, bits, blocks
-
-    def count(u_hat):
-        # all-zero codeword was sent: every 1 is a bit error (utils/metrics.py:94-144 semantics)
-        e = u_hat != 0
-        counters[0] += e.sum()
-        counters[1] += e.any(dim=-1).sum()
-        counters[2] += u_hat.numel()
-        counters[3] += u_hat.shape[0]
+    # Synthetic inputs, generated once on the device by the package's own transmit chain (per-rank Philox stream):
+    # BinarySource -> LDPC5GEncoder -> QPSK Mapper -> AWGN(Eb/N0 = 2 dB) -> Demapper("app"). Two distinct input sets
+    # (2 x 138 MB > 126 MB L2) are alternated between steps: nothing the decoder reads can be an L2 hit left over
+    # from the previous step.
+    sb_config.seed = 100 + 1000 * rank
+    no = ebnodb2no(EBNO_DB, 2, K_INFO / N_CODE)
+    src, mapper, demapper, awgn = BinarySource(), Mapper("qam", 2), Demapper("app", "qam", 2), AWGN()
+    d_u, d_in = [], []
+    for _ in range(2):
+        u = src([BATCH, K_INFO])
+        d_u.append(u)
+        d_in.append(demapper(awgn(mapper(enc(u)), no), no))
+    h_in = [t.cpu().pin_memory() for t in d_in]
+    counter = ErrorCounter(dev)                                   # device int64[4]: bit errors, block errors, bits, blocks
+    reduced = torch.zeros(4, dtype=torch.int64, device=dev)
 
     def step(i):
         u_hat = dec(d_in[i & 1])
-        count(u_hat)
+        counter.update(d_u[i & 1], u_hat)                         # sb_count_errors
         if world > 1:
-            dist.all_reduce(counters_step.copy_(counters), op=dist.ReduceOp.SUM)
+            dist.all_reduce(reduced.copy_(counter.counters), op=dist.ReduceOp.SUM)
         return u_hat
 
-    counters_step = torch.zeros_like(counters)
     for i in range(args.warmup):
         step(i)
+    counter.reset()
     torch.cuda.synchronize()
 
-    # ---- kernel-only timing for the roofline: CUDA events on the launching stream around the decode call ------
+    # ---- timed region: K steps; CUDA events on the launching stream around every decode call for the roofline --------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -189,9 +196,9 @@ def main():
         ev[i][0].record()
         u_hat = dec(d_in[i & 1])
         ev[i][1].record()
-        count(u_hat)
+        counter.update(d_u[i & 1], u_hat)
         if world > 1:
-            dist.all_reduce(counters_step.copy_(counters), op=dist.ReduceOp.SUM)
+            dist.all_reduce(reduced.copy_(counter.counters), op=dist.ReduceOp.SUM)
     t_stop.record()
     launches = _lib.lib().sb_launch_count() - launches0
     torch.cuda.synchronize()
@@ -205,20 +212,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * BATCH * N_CODE * args.steps / (ms_total * 1e-3)
+    if world > 1:
+        dist.all_reduce(reduced.copy_(counter.counters), op=dist.ReduceOp.SUM)
+        totals = reduced.cpu().tolist()
+    else:
+        totals = counter.counters.cpu().tolist()
 
-    # ---- end to end through the public API with HOST buffers: H2D of the logits, decode, D2H of the bits ------
-    h_out = torch.empty((BATCH, K_INFO), dtype=torch.float32).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    # ---- end to end through the public API with HOST buffers: every step copies its logits from pinned host memory to
+    # the device, decodes, and copies the decoded bits back to pinned host memory. Two streams are used round-robin so the
+    # copies of one step overlap the kernel of the other (a double-buffered serving loop).
+    h_out = [torch.empty((BATCH, K_INFO), dtype=torch.float32).pin_memory() for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    e2e_steps = max(4, min(args.steps, 10))
+
+    def e2e_step(i):
+        with torch.cuda.stream(streams[i & 1]):
+            x = h_in[i & 1].to(dev, non_blocking=True)
+            h_out[i & 1].copy_(dec(x), non_blocking=True)
+
     for i in range(2):
-        h_out.copy_(dec(h_in[i & 1].to(dev, non_blocking=True)), non_blocking=True)
+        e2e_step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    for s_ in streams:
+        s_.wait_event(e0)
     for i in range(e2e_steps):
-        x = h_in[i & 1].to(dev, non_blocking=True)
-        h_out.copy_(dec(x), non_blocking=True)
+        e2e_step(i)
+    for s_ in streams:
+        torch.cuda.current_stream().wait_stream(s_)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -229,20 +253,21 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = ALG_BYTES_PER_CW * BATCH / (kern_ms * 1e-3) / 1e9
-        c = counters.cpu().tolist()
+        c = totals
         line = {
             "metric": "coded bits/s, LDPC5G n=8448 k=4224 BP-20 decode", "value": value, "unit": "coded bits/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: LDPC5GDecoder(LDPC5GEncoder(4224,8448)), cn_update={args.cn_update}, "
                                    f"20 BP iterations, batch 4096 per GPU, AWGN Eb/N0 2 dB",
-                       "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}",
+                       "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}", "ebno_db": EBNO_DB,
                        "l2": "2 alternating input sets of 138 MB each (> 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "ldpc_bp_kernel",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_CW * BATCH},
             "e2e": {"value": e2e_val, "unit": "coded bits/s", "h2d_bytes_per_step": BATCH * N_CODE * 4,
-                    "d2h_bytes_per_step": BATCH * K_INFO * 4, "steps": e2e_steps},
+                    "d2h_bytes_per_step": BATCH * K_INFO * 4, "steps": e2e_steps,
+                    "pipeline": "2 CUDA streams, double-buffered pinned host buffers"},
             "gpu_launches": launches, "clocks": clocks,
             "ber": {"bit_errors": c[0], "block_errors": c[1], "bits": c[2], "blocks": c[3]},
         }
@@ -256,7 +281,7 @@ def main():
             t0 = time.perf_counter()
             u_ref = ref(x, num_threads=cores)
             dt = time.perf_counter() - t0
-            u_gpu = dec(d_in[0][:sample]).cpu().numpy()
+            u_gpu = dec(d_in[0][:sample].contiguous()).cpu().numpy()
             line["cpu_baseline"] = {"value": sample * N_CODE / dt, "unit": "coded bits/s", "cores": cores,
                                     "kind": "port",
                                     "sample": f"first {sample} codewords of the step-0 batch, oracle/ldpc_bp_ref.c libm "
