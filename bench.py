@@ -124,6 +124,9 @@ def main():
                     choices=["boxplus-phi", "boxplus", "minsum", "offset-minsum"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="codewords for the cpu_baseline leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ebno-db", type=float, default=EBNO_DB,
+                    help="Eb/N0 of the synthetic inputs (default 2 dB, SURVEY.md section 8d). The boxplus-phi kernel skips "
+                         "provably-zero phi terms of saturated messages, so its speed depends on how early codewords converge")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -158,7 +161,7 @@ def main():
     # (2 x 138 MB > 126 MB L2) are alternated between steps: nothing the decoder reads can be an L2 hit left over
     # from the previous step.
     sb_config.seed = 100 + 1000 * rank
-    no = ebnodb2no(EBNO_DB, 2, K_INFO / N_CODE)
+    no = ebnodb2no(args.ebno_db, 2, K_INFO / N_CODE)
     src, mapper, demapper, awgn = BinarySource(), Mapper("qam", 2), Demapper("app", "qam", 2), AWGN()
     d_u, d_in = [], []
     for _ in range(2):
@@ -259,8 +262,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: LDPC5GDecoder(LDPC5GEncoder(4224,8448)), cn_update={args.cn_update}, "
-                                   f"20 BP iterations, batch 4096 per GPU, AWGN Eb/N0 2 dB",
-                       "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}", "ebno_db": EBNO_DB,
+                                   f"20 BP iterations, batch 4096 per GPU, QPSK/AWGN Eb/N0 {args.ebno_db:g} dB",
+                       "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}", "ebno_db": args.ebno_db,
                        "l2": "2 alternating input sets of 138 MB each (> 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "ldpc_bp_kernel",

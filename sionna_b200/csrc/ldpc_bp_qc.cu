@@ -54,8 +54,20 @@ struct QcParams {
 // (c2v messages may be -0.0f; the VN arithmetic does not depend on the sign of a zero.)
 
 // ---- check-node updates on the edges pm[0], pm[Z], pm[2Z], ... of one check ------------------------------------
-// boxplus-phi (decoding.py:1126-1166), two edges per step on the packed fp32x2 pipe (sb_math2.cuh)
-__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip) {
+// boxplus-phi (decoding.py:1126-1166), two edges per step on the packed fp32x2 pipe (sb_math2.cuh).
+// Exact strength reductions (outputs are bit-identical, only instructions are saved), all decided warp-uniformly:
+//   (1) |x| >= 16.635532 (the phi clipping bound, :1113)  =>  phi(|x|) == 0 exactly              [saturated inputs]
+//   (2) p_e == 0  =>  P - p_e == P exactly  =>  phi(P - p_e) == phi(P), evaluated once per check
+//   (3) P - p_e <= 8.5e-8 (lower clipping bound)  =>  phi(P - p_e) == phi(8.5e-8) == phi_max
+// Once a codeword has converged every VN->CN message except those of degree-1 VNs sits at +-llr_max >= 16.64, and a
+// check costs ~3 phi evaluations instead of 2*deg; the per-iteration cost therefore depends on the channel SNR.
+#define SB_PHI_HI 16.635532f
+#define SB_PHI_LO 8.5e-8f
+// SC = false: plain evaluation; one vote per check on its first edge pair probes for saturation and raises *sat_flag,
+// which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
+template <bool SC>
+__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag) {
+    const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
     int l = 0;
@@ -65,7 +77,14 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip)
         float* q1 = q0 + Z;
         unsigned b0 = __float_as_uint(*q0), b1 = __float_as_uint(*q1);
         par ^= b0 ^ b1;
-        float2 p = sb_phif2(make_float2(__uint_as_float(b0 & 0x7fffffffu), __uint_as_float(b1 & 0x7fffffffu)));
+        float a0 = __uint_as_float(b0 & 0x7fffffffu), a1 = __uint_as_float(b1 & 0x7fffffffu);
+        float2 p = make_float2(0.f, 0.f);
+        if (SC) {
+            if (!__all_sync(am, a0 >= SB_PHI_HI && a1 >= SB_PHI_HI)) p = sb_phif2(make_float2(a0, a1));   // (1)
+        } else {
+            p = sb_phif2(make_float2(a0, a1));
+            if (l == 0 && __all_sync(am, a0 >= SB_PHI_HI && a1 >= SB_PHI_HI)) *sat_flag = 1;   // probe (benign race)
+        }
         P = __fadd_rn(P, p.x);                            // :1150 sequential sum, ascending VN
         P = __fadd_rn(P, p.y);
         *q0 = __uint_as_float(__float_as_uint(p.x) | (b0 & 0x80000000u));   // phi >= 0: sign bit carries sign(x)
@@ -75,27 +94,46 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip)
         float* q0 = pm + l * Z;
         unsigned b0 = __float_as_uint(*q0);
         par ^= b0;
-        float p = sb_phif(__uint_as_float(b0 & 0x7fffffffu));
+        float a0 = __uint_as_float(b0 & 0x7fffffffu);
+        float p = 0.f;
+        if (!SC || !__all_sync(am, a0 >= SB_PHI_HI)) p = sb_phif(a0);
         P = __fadd_rn(P, p);
         *q0 = __uint_as_float(__float_as_uint(p) | (b0 & 0x80000000u));
     }
     par &= 0x80000000u;
+    float yP = 0.f;                                       // phi(P), evaluated lazily (2)
+    bool have_yP = false;
     l = 0;
 #pragma unroll 2
     for (; l + 1 < deg; l += 2) {
         float* q0 = pm + l * Z;
         float* q1 = q0 + Z;
         unsigned b0 = __float_as_uint(*q0), b1 = __float_as_uint(*q1);
-        float2 m = __fadd2_rn(make_float2(__uint_as_float(b0 | 0x80000000u), __uint_as_float(b1 | 0x80000000u)),
-                              make_float2(P, P));         // (-p) + P  (:1155)
-        float2 y = sb_phif2(m);
+        float2 y;
+        if (SC && __all_sync(am, ((b0 | b1) & 0x7fffffffu) == 0u)) {                                 // (2)
+            if (!have_yP) { yP = sb_phif(P); have_yP = true; }
+            y = make_float2(yP, yP);
+        } else {
+            float2 m = __fadd2_rn(make_float2(__uint_as_float(b0 | 0x80000000u), __uint_as_float(b1 | 0x80000000u)),
+                                  make_float2(P, P));     // (-p) + P  (:1155)
+            if (SC && __all_sync(am, m.x <= SB_PHI_LO && m.y <= SB_PHI_LO)) y = make_float2(phi_max, phi_max);   // (3)
+            else y = sb_phif2(m);
+        }
         *q0 = __uint_as_float(__float_as_uint(fminf(y.x, clip)) | ((b0 ^ par) & 0x80000000u));   // :1161-1163
         *q1 = __uint_as_float(__float_as_uint(fminf(y.y, clip)) | ((b1 ^ par) & 0x80000000u));
     }
     if (l < deg) {
         float* q0 = pm + l * Z;
         unsigned b0 = __float_as_uint(*q0);
-        float y = sb_phif(__fadd_rn(__uint_as_float(b0 | 0x80000000u), P));
+        float y;
+        if (SC && __all_sync(am, (b0 & 0x7fffffffu) == 0u)) {
+            if (!have_yP) { yP = sb_phif(P); have_yP = true; }
+            y = yP;
+        } else {
+            float m = __fadd_rn(__uint_as_float(b0 | 0x80000000u), P);
+            if (SC && __all_sync(am, m <= SB_PHI_LO)) y = phi_max;
+            else y = sb_phif(m);
+        }
         *q0 = __uint_as_float(__float_as_uint(fminf(y, clip)) | ((b0 ^ par) & 0x80000000u));
     }
 }
@@ -178,8 +216,12 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
 }
 
 template <int RULE, int CLS>
-__device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset) {
-    if (RULE == SB_CN_BOXPLUS_PHI) cn_phi_qc(pm, Z, deg, clip);
+__device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset, float phi_max, bool sc,
+                                      int* sat_flag) {
+    if (RULE == SB_CN_BOXPLUS_PHI) {
+        if (sc) cn_phi_qc<true>(pm, Z, deg, clip, phi_max, sat_flag);
+        else cn_phi_qc<false>(pm, Z, deg, clip, phi_max, sat_flag);
+    }
     else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
         const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
@@ -301,12 +343,13 @@ __device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx&
 
 template <int RULE, int CLS>
 __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
-                                         const int4* s_row, int start, int end, float clip, bool fuse) {
+                                         const int4* s_row, int start, int end, float clip, bool fuse,
+                                         float phi_max, bool sc, int* sat_flag) {
     for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
         int4 ri = s_row[rr];
         if (w.lane_i < ri.z) {
             float* pm = msg + ri.x * p.Z + w.lane_i;
-            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset);
+            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag);
             if (fuse && ri.w >= 0) {
                 // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
                 // with a single incoming message) so the VN phase can skip the column
@@ -378,6 +421,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     int4* s_row = reinterpret_cast<int4*>(smem_raw + off_row);
     int2* s_ce_p = reinterpret_cast<int2*>(smem_raw + off_ce);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
+    int* sat_flag = reinterpret_cast<int*>(smem_raw + off_bar + 8);
     const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
     const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
@@ -396,6 +440,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     __syncthreads();
 
     const float clip = p.llr_max;
+    const float phi_max = sb_phif(0.f);                   // phi at its lower clipping bound
     uint32_t tma_phase = 0;
 
     for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -422,6 +467,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
             }
         }
         __syncthreads();
+        if (tid == 0) *sat_flag = 0;
         // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
         vn_all<1>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
         __syncthreads();
@@ -436,13 +482,14 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
         }
         for (int it = 0; it < p.num_iter; ++it) {
             const bool final_pass = it == p.num_iter - 1;
+            const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
             const int* re = p.row_cls_end;
-            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass);
-            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass);
-            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass);
-            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass);
-            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass);
+            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag);
+            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag);
+            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag);
+            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag);
+            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag);
             __syncthreads();
             // ---- VN phase ---------------------------------------------------------------------------------------
             vn_all<0>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
