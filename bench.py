@@ -28,6 +28,17 @@ E_EDGES, N_VNS = 40320, 8832
 ALG_BYTES_PER_CW = NUM_ITER * (8 * E_EDGES + 4 * N_VNS) + 4 * N_CODE + 4 * K_INFO      # 7 208 448
 
 
+def measured_traffic(cn_update):
+    """DRAM bytes per launch of the decode kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if cn_update in d:
+            return d[cn_update]["traffic_bytes_per_launch"]
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -266,7 +277,8 @@ def main():
                        "cn_update": args.cn_update, "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}", "ebno_db": args.ebno_db,
                        "l2": "2 alternating input sets of 138 MB each (> 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ldpc_bp_kernel",
+                         "traffic": measured_traffic(args.cn_update), "peak_source": peak_src,
+                         "kernel": "ldpc_bp_qc_kernel",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_CW * BATCH},
             "e2e": {"value": e2e_val, "unit": "coded bits/s", "h2d_bytes_per_step": BATCH * N_CODE * 4,
                     "d2h_bytes_per_step": BATCH * K_INFO * 4, "steps": e2e_steps,
