@@ -286,6 +286,24 @@ def main():
             "gpu_launches": launches, "clocks": clocks,
             "ber": {"bit_errors": c[0], "block_errors": c[1], "bits": c[2], "blocks": c[3]},
         }
+        # the north-star's min-sum rule on the same inputs (the headline rule above is the reference's default boxplus-phi)
+        if args.cn_update != "minsum":
+            dec_ms = LDPC5GDecoder(enc, cn_update="minsum", num_iter=NUM_ITER, hard_out=True, return_infobits=True)
+            for i in range(3):
+                dec_ms(d_in[i & 1])
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a0.record()
+            for i in range(reps):
+                dec_ms(d_in[i & 1])
+            a1.record()
+            torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1) / reps
+            line["other_rules"] = {"minsum": {"value": BATCH * N_CODE / (ms * 1e-3), "unit": "coded bits/s (1 GPU, device)",
+                                              "kernel_ms": ms,
+                                              "roofline_frac": ALG_BYTES_PER_CW * BATCH / (ms * 1e-3) / 1e9 / peak,
+                                              "traffic": measured_traffic("minsum")}}
         if not args.no_cpu_baseline:
             from oracle import ldpc as O
             cores = os.cpu_count() or 1

@@ -150,18 +150,29 @@ int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, i
  * d_counters[0] += #(b != b_hat); [1] += #rows with any difference; [2] += rows*k; [3] += rows  (int64[4], device). */
 int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_t k, int64_t* d_counters, void* stream);
 
+/* CRCEncoder.call (fec/crc.py:175-215): d_bits [rows, k] -> d_out [rows, k + crc_length] = [bits | CRC parity];
+ * d_gen_rows[k]: row i of the reference's generator matrix (crc.py:126-156) packed MSB-first into 32 bits. */
+int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, int32_t k, int32_t crc_length, float* d_out,
+                  int64_t rows, void* stream);
+/* TB5GScrambler.call (fec/scrambling.py:442-468): d_x [rows, n], d_seq [seq_rows, n] Gold sequence(s) (nr/utils.py:16-76);
+ * binary != 0: |x - c|, else x * (1 - 2c); row r uses sequence r mod seq_rows. */
+int sb_scramble(const float* d_x, const float* d_seq, int32_t binary, float* d_out, int64_t rows, int32_t n,
+                int32_t seq_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * OFDM, resource grid, channel estimation, MIMO equalisation (complex64 = interleaved float pairs)
  * ---------------------------------------------------------------------------------------------- */
 /* OFDMModulator.call (ofdm/modulator.py:97-124): d_x [rows, num_symbols, fft_size] frequency-domain grid (DC centred)
  * -> d_out [rows, out_len]; symbol l starts at d_out_off[l] and carries d_cp[l] cyclic-prefix samples:
- * ifftshift, ifft * sqrt(N) (signal/utils.py:206-249), CP = last cp samples prepended. Any fft_size <= 8192. */
+ * ifftshift, ifft * sqrt(N) (signal/utils.py:206-249), CP = last cp samples prepended. Any fft_size <= 8192.
+ * shift = 0 skips the (i)fftshift: with cp = 0 the two functions are then signal.ifft / signal.fft (signal/utils.py:161-249). */
 int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
-                     const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, void* stream);
+                     const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, int32_t shift, void* stream);
 /* OFDMDemodulator.call (ofdm/demodulator.py:162-203): d_x [rows, in_len] time samples -> d_out [rows, num_symbols,
  * fft_size]: CP removal, fft / sqrt(N), phase compensation exp(-j 2 pi k l_min / N), fftshift. */
 int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
-                       const int32_t* d_cp, const int32_t* d_in_off, int32_t in_len, int32_t l_min, void* stream);
+                       const int32_t* d_cp, const int32_t* d_in_off, int32_t in_len, int32_t l_min, int32_t shift,
+                       void* stream);
 /* out[b, r, j] = in[b, (in_rows == 1 ? 0 : r), idx[r, j]] (0 where idx < 0); words = 1 (fp32) or 2 (complex64).
  * Replaces the tf.gather re-indexing of RemoveNulledSubcarriers (ofdm/resource_grid.py:551), ResourceGridDemapper
  * (:466-520) and NearestNeighborInterpolator (ofdm/channel_estimation.py:409-435). */

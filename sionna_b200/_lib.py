@@ -38,8 +38,10 @@ SIGNATURES = {
     "sb_demap": (i32, [vp, vp, i64, vp, i32, i32, vp, i64, vp, i64, i32, vp]),
     "sb_awgn": (i32, [vp, vp, i64, vp, i64, u64, u64, vp]),
     "sb_count_errors": (i32, [vp, vp, i64, i32, vp, vp]),
-    "sb_ofdm_modulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, vp]),
-    "sb_ofdm_demodulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, i32, vp]),
+    "sb_crc_encode": (i32, [vp, vp, i32, i32, vp, i64, vp]),
+    "sb_scramble": (i32, [vp, vp, i32, vp, i64, i32, i32, vp]),
+    "sb_ofdm_modulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, i32, vp]),
+    "sb_ofdm_demodulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, i32, i32, vp]),
     "sb_gather_rows": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "sb_rg_map": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "sb_ls_at_pilots": (i32, [vp, vp, vp, vp, i64, vp, vp, i64, i32, i32, i32, vp]),

@@ -92,7 +92,8 @@ __device__ void fft_inplace_smem(float2* buf0, float2* buf1, const float2* W, co
 // OFDMModulator: x [rows, nsym, N] (frequency domain, DC in the centre) -> out [rows, sum_l (N + cp[l])]
 // ifftshift -> ifft * sqrt(N) -> cyclic prefix (modulator.py:100-124, signal/utils.py:240-249).
 __global__ void ofdm_mod_kernel(const float2* __restrict__ x, float2* __restrict__ out, FftPlan plan, int nsym,
-                                const int* __restrict__ cp, const int* __restrict__ out_off, int out_len, long long rows) {
+                                const int* __restrict__ cp, const int* __restrict__ out_off, int out_len, long long rows,
+                                int shift) {
     extern __shared__ float2 sm[];
     const int N = plan.n, tid = threadIdx.x, T = blockDim.x;
     float2* b0 = sm; float2* b1 = sm + N; float2* W = sm + 2 * N;
@@ -107,7 +108,7 @@ __global__ void ofdm_mod_kernel(const float2* __restrict__ x, float2* __restrict
         const float2* src = x + job * N;
         __syncthreads();
         for (int k = tid; k < N; k += T) {
-            float2 v = src[(k + N / 2) % N];        // ifftshift: out[k] = in[(k + floor(N/2)) mod N]
+            float2 v = src[shift ? (k + N / 2) % N : k];   // ifftshift: out[k] = in[(k + floor(N/2)) mod N]
             b0[k] = make_float2(v.x, -v.y);
         }
         __syncthreads();
@@ -126,7 +127,7 @@ __global__ void ofdm_mod_kernel(const float2* __restrict__ x, float2* __restrict
 // exp(-j 2 pi k l_min / N) (fp32 table, demodulator.py:131-134, 196-198), fftshift (:201).
 __global__ void ofdm_demod_kernel(const float2* __restrict__ x, float2* __restrict__ out, FftPlan plan, int nsym,
                                   const int* __restrict__ cp, const int* __restrict__ in_off, int in_len, int l_min,
-                                  long long rows) {
+                                  long long rows, int shift) {
     extern __shared__ float2 sm[];
     const int N = plan.n, tid = threadIdx.x, T = blockDim.x;
     float2* b0 = sm; float2* b1 = sm + N; float2* W = sm + 2 * N; float2* PC = sm + 3 * N;
@@ -149,7 +150,7 @@ __global__ void ofdm_demod_kernel(const float2* __restrict__ x, float2* __restri
         fft_inplace_smem(b0, b1, W, plan, &res);
         float2* dst = out + job * N;
         for (int k = tid; k < N; k += T) {
-            int ks = (k + N / 2) % N;               // fftshift: out[k'] with k' = (k + floor(N/2)) mod N takes bin k
+            int ks = shift ? (k + N / 2) % N : k;   // fftshift: out[k'] with k' = (k + floor(N/2)) mod N takes bin k
             float2 v = cmul(cscale(res[k], scale), PC[k]);
             dst[ks] = v;
         }
@@ -466,7 +467,7 @@ int make_plan(int n, FftPlan* plan) {
 }  // namespace
 
 extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
-                                const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, void* stream) {
+                                const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, int32_t shift, void* stream) {
     SB_CHECK_ARG(d_x && d_out && d_cp && d_out_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_modulate: bad arguments");
     if (rows == 0) return SB_OK;
@@ -478,14 +479,14 @@ extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, in
     long long jobs = rows * num_symbols;
     int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 8);
     ofdm_mod_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>((const float2*)d_x, (float2*)d_out, plan, num_symbols,
-                                                                   d_cp, d_out_off, out_len, rows);
+                                                                   d_cp, d_out_off, out_len, rows, shift);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
 
 extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
                                   const int32_t* d_cp, const int32_t* d_in_off, int32_t in_len, int32_t l_min,
-                                  void* stream) {
+                                  int32_t shift, void* stream) {
     SB_CHECK_ARG(d_x && d_out && d_cp && d_in_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_demodulate: bad arguments");
     if (rows == 0) return SB_OK;
@@ -497,7 +498,7 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
     long long jobs = rows * num_symbols;
     int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 8);
     ofdm_demod_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>((const float2*)d_x, (float2*)d_out, plan,
-                                                                     num_symbols, d_cp, d_in_off, in_len, l_min, rows);
+                                                                     num_symbols, d_cp, d_in_off, in_len, l_min, rows, shift);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -196,6 +196,41 @@ __global__ void count_errors_kernel(const float* __restrict__ b, const float* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CRCEncoder.call (fec/crc.py:175-215): the reference multiplies the bit row with a dense [k, L] generator matrix and
+// reduces mod 2; the CRC is linear, so the parity word is the XOR of the (bit-packed) matrix rows selected by the set
+// bits. One warp per row: lanes stride over the k bits, XOR-reduce, then write [bits | parity] (MSB = first parity bit).
+__global__ void crc_encode_kernel(const float* __restrict__ bits, const unsigned* __restrict__ gtab, int k, int L,
+                                  float* __restrict__ out, long long rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (long long r = (long long)blockIdx.x * nwarps + warp; r < rows; r += (long long)gridDim.x * nwarps) {
+        const float* b = bits + r * k;
+        float* o = out + r * (long long)(k + L);
+        unsigned acc = 0;
+        for (int i = lane; i < k; i += 32) {
+            float v = b[i];
+            o[i] = v;
+            if (((int)v) & 1) acc ^= gtab[i];
+        }
+        acc = __reduce_xor_sync(0xffffffffu, acc);
+        if (lane < L) o[k + lane] = (float)((acc >> (L - 1 - lane)) & 1u);
+    }
+}
+
+// TB5GScrambler.call (fec/scrambling.py:442-468): binary: |x - c|; soft values: x * (1 - 2c). seq has seq_rows rows
+// (one per stream) of length n; row r of x uses seq row (r mod seq_rows).
+__global__ void scramble_kernel(const float* __restrict__ x, const float* __restrict__ seq, int binary,
+                                float* __restrict__ out, long long rows, int n, int seq_rows) {
+    const long long total = rows * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(i % n);
+        long long r = i / n;
+        float c = seq[(r % seq_rows) * n + j];
+        float v = x[i];
+        out[i] = binary ? fabsf(v - c) : v * (-2.f * c + 1.f);
+    }
+}
+
 inline int grid_for(long long work_items, int threads) {
     int sms = sb_num_sms();
     long long blocks = (work_items + threads - 1) / threads;
@@ -270,6 +305,25 @@ extern "C" int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t r
     if (rows == 0) return SB_OK;
     count_errors_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         d_b, d_b_hat, rows, k, (unsigned long long*)d_counters);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, int32_t k, int32_t crc_length, float* d_out,
+                             int64_t rows, void* stream) {
+    SB_CHECK_ARG(d_bits && d_gen_rows && d_out && k >= 1 && crc_length >= 1 && crc_length <= 32 && rows >= 0,
+                 "sb_crc_encode: bad arguments");
+    if (rows == 0) return SB_OK;
+    crc_encode_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(d_bits, d_gen_rows, k, crc_length, d_out, rows);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_scramble(const float* d_x, const float* d_seq, int32_t binary, float* d_out, int64_t rows, int32_t n,
+                           int32_t seq_rows, void* stream) {
+    SB_CHECK_ARG(d_x && d_seq && d_out && rows >= 0 && n >= 1 && seq_rows >= 1, "sb_scramble: bad arguments");
+    if (rows == 0) return SB_OK;
+    scramble_kernel<<<grid_for(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_seq, binary, d_out, rows, n, seq_rows);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

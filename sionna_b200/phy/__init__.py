@@ -7,3 +7,4 @@ from . import channel
 from . import fec
 from . import mimo
 from . import ofdm
+from . import signal

@@ -61,5 +61,5 @@ class OFDMDemodulator(Block):
         rows = x.numel() // ns
         out = torch.empty(list(x.shape[:-1]) + [nsym, self._fft_size], dtype=torch.complex64, device=dev)
         check(lib().sb_ofdm_demodulate(ptr(x), ptr(out), rows, nsym, self._fft_size, ptr(self._tabs[0]),
-                                       ptr(self._tabs[1]), ns, self._l_min, current_stream()), "sb_ofdm_demodulate")
+                                       ptr(self._tabs[1]), ns, self._l_min, 1, current_stream()), "sb_ofdm_demodulate")
         return out

@@ -54,6 +54,6 @@ class OFDMModulator(Block):
             self._tabs = (torch.from_numpy(np.ascontiguousarray(cp)).to(dev), torch.from_numpy(off).to(dev), (nsym, n, dev))
         rows = x.numel() // (nsym * n)
         out = torch.empty(list(x.shape[:-2]) + [out_len], dtype=torch.complex64, device=dev)
-        check(lib().sb_ofdm_modulate(ptr(x), ptr(out), rows, nsym, n, ptr(self._tabs[0]), ptr(self._tabs[1]), out_len,
+        check(lib().sb_ofdm_modulate(ptr(x), ptr(out), rows, nsym, n, ptr(self._tabs[0]), ptr(self._tabs[1]), out_len, 1,
                                      current_stream()), "sb_ofdm_modulate")
         return out

@@ -1,0 +1,82 @@
+"""CRC and TB scrambling (SURVEY.md section 8(f2) pieces): host logic on CPU, kernels on the GPU."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle import nr as R
+
+POLS = ["CRC24A", "CRC24B", "CRC24C", "CRC16", "CRC11", "CRC6"]
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "crc_golden.npz")
+
+
+def test_crc_oracle_and_generator_rows_vs_reference_vectors():
+    from sionna_b200.phy.fec.crc import CRCEncoder
+    g = np.load(GOLD)
+    rng = np.random.default_rng(0)
+    for pol in POLS:
+        u, x = g[f"u_{pol}"], g[f"x_{pol}"]
+        assert np.array_equal(R.crc_parity(u[0], pol), x)                       # oracle vs the reference's KAT
+        enc = CRCEncoder(pol)
+        assert enc.crc_length == len(x)
+        for k in (10, 57, 1000):                                                # product's packed generator rows vs oracle
+            rows = enc._gen_rows(k)
+            b = rng.integers(0, 2, k)
+            acc = np.bitwise_xor.reduce(np.where(b.astype(bool), rows, 0).astype(np.uint32))
+            par = (acc >> np.arange(enc.crc_length - 1, -1, -1)) & 1
+            assert np.array_equal(par, R.crc_parity(b, pol))
+
+
+def test_prng_sequence_matches_literal_restatement():
+    from sionna_b200.phy.fec.scrambling import generate_prng_seq, TB5GScrambler
+    for c_init in (0, 1, 1000, 2 ** 31 - 1, 12345678):
+        assert np.array_equal(generate_prng_seq(500, c_init), R.generate_prng_seq(500, c_init))
+    with pytest.raises(ValueError):
+        TB5GScrambler(n_rnti=70000)
+    with pytest.raises(ValueError):
+        TB5GScrambler(n_id=1024)
+    with pytest.raises(TypeError):
+        TB5GScrambler(channel_type="PUCCH")
+
+
+@pytest.mark.gpu
+def test_crc_kernels(cuda_device):
+    from sionna_b200.phy.fec.crc import CRCEncoder, CRCDecoder
+    g = np.load(GOLD)
+    rng = np.random.default_rng(1)
+    for pol in POLS:
+        enc = CRCEncoder(pol)
+        x = enc(torch.from_numpy(g[f"u_{pol}"].astype(np.float32)).to(cuda_device)).cpu().numpy()
+        assert np.array_equal(x.reshape(-1)[-enc.crc_length:], g[f"x_{pol}"])   # test_crc.py:177-199
+        assert enc.k == 10 and enc.n == 10 + enc.crc_length
+        dec = CRCDecoder(enc)
+        for shape in ([100], [100, 10], [4, 2, 100], [1, 100000]):
+            u = rng.integers(0, 2, shape).astype(np.float32)
+            xc = enc(torch.from_numpy(u).to(cuda_device))
+            assert np.array_equal(xc.cpu().numpy(), R.crc_encode(u, pol)) if np.prod(shape) <= 4000 else True
+            u2, ok = dec(xc)
+            assert bool(ok.all()) and np.array_equal(u2.cpu().numpy(), u) and ok.shape == tuple(shape[:-1]) + (1,)
+        xe = enc(torch.from_numpy(rng.integers(0, 2, (200, 64)).astype(np.float32)).to(cuda_device)).clone()
+        pos = torch.from_numpy(rng.integers(0, xe.shape[-1], 200)).to(cuda_device)
+        xe[torch.arange(200, device=cuda_device), pos] = 1 - xe[torch.arange(200, device=cuda_device), pos]
+        assert not bool(dec(xe)[1].any())                                       # every single-bit error is detected
+
+
+@pytest.mark.gpu
+def test_scrambler_kernel(cuda_device):
+    from sionna_b200.phy.fec.scrambling import TB5GScrambler
+    rng = np.random.default_rng(2)
+    b = rng.integers(0, 2, (5, 3, 700)).astype(np.float32)
+    s = TB5GScrambler(n_rnti=77, n_id=300)
+    y = s(torch.from_numpy(b).to(cuda_device))
+    seq = R.generate_prng_seq(700, 77 * 2 ** 15 + 300).astype(np.float32)
+    assert np.array_equal(y.cpu().numpy(), np.abs(b - seq))
+    assert np.array_equal(s(y).cpu().numpy(), b)                                # involution
+    llr = rng.normal(size=b.shape).astype(np.float32)
+    z = s(torch.from_numpy(llr).to(cuda_device), binary=False).cpu().numpy()
+    assert np.array_equal(z, llr * (1 - 2 * seq))
+    ms = TB5GScrambler(n_rnti=[1, 2, 3], n_id=[5, 6, 7], channel_type="PDSCH", codeword_index=1)
+    ym = ms(torch.from_numpy(b).to(cuda_device)).cpu().numpy()
+    for i, (nr, ni) in enumerate(zip([1, 2, 3], [5, 6, 7])):
+        sq = R.generate_prng_seq(700, nr * 2 ** 15 + 2 ** 14 + ni).astype(np.float32)
+        assert np.array_equal(ym[:, i], np.abs(b[:, i] - sq))

@@ -199,3 +199,16 @@ def test_ofdm_lmmse_equalizer_and_detector_vs_oracle(cuda_device, cfg):
     idx = np.argmin(np.abs(x_hat.cpu().numpy()[..., None] - pts), -1)
     if cfg != "siso":                                                        # (a single Rayleigh tap may be in a deep fade)
         assert np.mean(pts[idx] != xd) < 0.02
+
+
+def test_signal_fft_ifft(cuda_device):
+    """signal.fft / ifft: normalised DFT pair along an arbitrary axis (signal/utils.py:161-249)."""
+    from sionna_b200.phy.signal import fft, ifft
+    rng = np.random.default_rng(11)
+    x = _c64(rng, (3, 48, 5))
+    X = fft(torch.from_numpy(x).to(cuda_device), axis=1)
+    np.testing.assert_allclose(X.cpu().numpy(), np.fft.fft(x.astype(complex), axis=1) / np.sqrt(48), atol=2e-5)
+    np.testing.assert_allclose(ifft(X, axis=1).cpu().numpy(), x, atol=2e-5)
+    y = _c64(rng, (7, 100))
+    np.testing.assert_allclose(ifft(torch.from_numpy(y).to(cuda_device)).cpu().numpy(),
+                               np.fft.ifft(y.astype(complex)) * 10.0, atol=2e-5)
