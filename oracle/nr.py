@@ -44,3 +44,66 @@ def generate_prng_seq(length, c_init):
     for idx in range(length):
         c[idx] = np.mod(x1[idx + n_c] + x2[idx + n_c], 2)
     return c
+
+
+# ---- transport block chain (nr/tb_encoder.py:381-435, nr/utils.py:473-811) -------------------------------------------
+def tb_params(target_tb_size, num_coded_bits, target_coderate, m, num_layers):
+    """Literal float32 restatement of calculate_tb_size for one TB (utils.py:560-811)."""
+    f = np.float32
+    tbs_t, r = f(target_tb_size), f(target_coderate)
+    if tbs_t <= 3824:
+        n = np.maximum(f(3.0), f(np.floor(np.log(tbs_t) / f(np.log(2.0))) - 6))
+        n_info_q = np.maximum(f(24.0), f(2 ** n * np.floor(tbs_t / 2 ** n)))
+    else:
+        n = np.floor(np.log(tbs_t - f(24)) / np.log(f(2.0))) - 5.0
+        n_info_q = np.maximum(f(3840.0), f(2 ** n * np.round((tbs_t - 24) / 2 ** n)))
+    tab = [24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120, 128, 136, 144, 152, 160, 168, 176, 184, 192, 208, 224, 240,
+           256, 272, 288, 304, 320, 336, 352, 368, 384, 408, 432, 456, 480, 504, 528, 552, 576, 608, 640, 672, 704, 736, 768,
+           808, 848, 888, 928, 984, 1032, 1064, 1128, 1160, 1192, 1224, 1256, 1288, 1320, 1352, 1416, 1480, 1544, 1608, 1672,
+           1736, 1800, 1864, 1928, 2024, 2088, 2152, 2216, 2280, 2408, 2472, 2536, 2600, 2664, 2728, 2792, 2856, 2976, 3104,
+           3240, 3368, 3496, 3624, 3752, 3824]
+    if n_info_q <= 3824:
+        num_cb, tb_size = 1, min(t for t in tab if t >= n_info_q)
+    else:
+        num_cb = int(np.ceil((n_info_q + 24) / 3816)) if r <= 0.25 else (int(np.ceil((n_info_q + 24) / 8424)) if n_info_q > 8424 else 1)
+        tb_size = int(8 * num_cb * np.ceil((n_info_q + 24) / (8 * num_cb)) - 24)
+    tb_crc = 24 if tb_size > 3824 else 16
+    cb_crc = 24 if num_cb > 1 else 0
+    cb_size = int((tb_size + tb_crc) / num_cb) + cb_crc
+    q = num_layers * m
+    n_last = int(num_coded_bits / q) % num_cb
+    l_last = q * int(np.ceil(num_coded_bits / (q * num_cb)))
+    l_first = q * int(np.floor(num_coded_bits / (q * num_cb)))
+    return tb_size, cb_size, num_cb, tb_crc, cb_crc, [l_first] * (num_cb - n_last) + [l_last] * n_last
+
+
+def tb_encode(u, num_coded_bits, target_coderate, m, num_layers, n_rnti, n_id, scramble=True):
+    """[B, tb_size] -> [B, num_coded_bits] for one stream (tb_encoder.py:381-435)."""
+    from .ldpc import LDPC5GEncoderRef
+    u = np.asarray(u).astype(np.uint8)
+    tb_size, cb_size, num_cb, tb_crc, cb_crc, cw = tb_params(u.shape[-1], num_coded_bits, target_coderate, m, num_layers)
+    assert tb_size == u.shape[-1]
+    x = crc_encode(u, "CRC16" if tb_crc == 16 else "CRC24A").astype(np.uint8)
+    x = x.reshape(u.shape[0], num_cb, cb_size - cb_crc)
+    if cb_crc:
+        x = crc_encode(x, "CRC24B").astype(np.uint8)
+    n_max, n_min = max(cw), min(cw)
+    enc = LDPC5GEncoderRef(cb_size, n_max)
+    c = enc(x.reshape(-1, cb_size)).reshape(u.shape[0], num_cb * n_max)
+    def out_int(n):                                                  # encoding.py:238-244
+        perm = np.zeros(n, int)
+        for j in range(n // m):
+            for i in range(m):
+                perm[i + j * m] = i * (n // m) + j
+        return perm
+    perm, punc, pos = [], [], 0
+    for l in cw:
+        if l == n_min:
+            perm.append(out_int(n_min) + pos); punc.append(np.arange(pos + n_min, pos + n_max)); pos += n_max
+        else:
+            perm.append(out_int(n_max) + pos); pos += l
+    perm = np.concatenate(perm + punc).astype(int)
+    c = c[:, perm][:, :sum(cw)]
+    if scramble:
+        c = np.abs(c - generate_prng_seq(sum(cw), n_rnti * 2 ** 15 + n_id))
+    return c.astype(np.float32)
