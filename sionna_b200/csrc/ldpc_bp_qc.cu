@@ -163,7 +163,7 @@ __device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip
 // (deg-1)*llr_max < 99000, so the reference's 1e5 sentinel logic (decoding.py:849-887) reduces exactly to
 //   unique minimum -> that edge gets fl(fl(m2 - m1) + m1), all others m1;  repeated minimum -> all edges m1.
 // Offset, max(.,0) and clipping act on only two distinct magnitudes and are hoisted out of the edge loop.
-template <int DMAX>
+template <int DMAX, bool EXACT>                           // EXACT: deg == DMAX, no per-edge guards
 __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset) {
     float x[DMAX];                                        // every element is assigned unconditionally (registers)
     float m1 = INFINITY, m2 = INFINITY;
@@ -171,7 +171,7 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
 #pragma unroll
     for (int l = 0; l < DMAX; ++l) {
         float v = INFINITY;                               // neutral: never the minimum, sign +
-        if (l < deg) v = pm[l * Z];                       // warp-uniform predicate
+        if (EXACT || l < deg) v = pm[l * Z];              // warp-uniform predicate
         x[l] = v;
         float a = fabsf(v);
         m2 = fminf(m2, fmaxf(m1, a));
@@ -188,7 +188,7 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
         float v = x[l];
         float mag = (fabsf(v) == m1) ? oe : o1;
         float y = __uint_as_float(__float_as_uint(mag) | ((__float_as_uint(v) ^ par) & 0x80000000u));
-        if (l < deg) pm[l * Z] = y;
+        if (EXACT || l < deg) pm[l * Z] = y;
     }
 }
 
@@ -225,11 +225,24 @@ __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, flo
     else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
         const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
-        if (CLS == 4) cn_minsum_qc<4>(pm, Z, deg, clip, off);
-        else if (CLS == 3) cn_minsum_qc<8>(pm, Z, deg, clip, off);
-        else if (CLS == 2) cn_minsum_qc<12>(pm, Z, deg, clip, off);
-        else if (CLS == 1) cn_minsum_qc<20>(pm, Z, deg, clip, off);
-        else cn_minsum_qc_loop(pm, Z, deg, clip, off);
+        // exact-degree code for the degrees of the 5G base graphs, guarded buckets otherwise (deg is warp-uniform)
+        if (CLS == 4) {
+            if (deg == 3) cn_minsum_qc<3, true>(pm, Z, deg, clip, off);
+            else if (deg == 4) cn_minsum_qc<4, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<4, false>(pm, Z, deg, clip, off);
+        } else if (CLS == 3) {
+            if (deg == 5) cn_minsum_qc<5, true>(pm, Z, deg, clip, off);
+            else if (deg == 6) cn_minsum_qc<6, true>(pm, Z, deg, clip, off);
+            else if (deg == 7) cn_minsum_qc<7, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<8, true>(pm, Z, deg, clip, off);
+        } else if (CLS == 2) {
+            if (deg == 9) cn_minsum_qc<9, true>(pm, Z, deg, clip, off);
+            else if (deg == 10) cn_minsum_qc<10, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<12, false>(pm, Z, deg, clip, off);
+        } else if (CLS == 1) {
+            if (deg == 19) cn_minsum_qc<19, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<20, false>(pm, Z, deg, clip, off);
+        } else cn_minsum_qc_loop(pm, Z, deg, clip, off);
     }
 }
 
@@ -253,7 +266,7 @@ __device__ __forceinline__ int2 lds_i2(uint32_t a) {
 // Returns the unclipped x_tot. MODE 0: normal update; MODE 1: initialisation v2c = llr (decoding.py:571).
 // Branch free: table entries beyond the column's degree are not read (predicate), their slot address points at the
 // VN's own first edge and the accumulate / store are predicated off.
-template <int DMAX, bool CHECK, bool KEEPM, int MODE>
+template <int DMAX, bool CHECK, bool KEEPM, int MODE, bool EXACT = false>   // EXACT: deg == DMAX and !CHECK: no guards
 __device__ __forceinline__ float vn_qc(uint32_t msg_s, uint32_t ce_s, int deg, int j4, int Z4, float llr, float clip) {
     uint32_t addr[DMAX];
     float m[KEEPM ? DMAX : 1];
@@ -262,10 +275,10 @@ __device__ __forceinline__ float vn_qc(uint32_t msg_s, uint32_t ce_s, int deg, i
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) {
         int2 e = make_int2(0, 0);
-        if (k < deg) e = lds_i2(ce_s + 8 * k);            // warp-uniform predicate
+        if (EXACT || k < deg) e = lds_i2(ce_s + 8 * k);   // warp-uniform predicate
         int t = j4 - (e.y & 0xffff);
         t += (t >> 31) & Z4;                              // (j - s) mod Z, in bytes
-        bool ok = (k < deg) && (!CHECK || t < (int)((unsigned)e.y >> 16));   // edge exists
+        bool ok = EXACT || ((k < deg) && (!CHECK || t < (int)((unsigned)e.y >> 16)));   // edge exists
         on[k] = ok;
         addr[k] = msg_s + e.x + t;
         float v = 0.f;
@@ -317,14 +330,32 @@ __device__ __forceinline__ float vn_qc_loop(uint32_t msg_s, uint32_t ce_s, int d
 
 // VN classes (host: col_class()): 0 loop (deg > 32), 1 <=32, 2 <=20, 3 <=12, 4 <=8, 5 <=4, 6 <=2; with edges into a
 // pruning-cut row: 7 loop, 8 <=12, 9 <=4; 10: degree-1 columns whose update is fused into the CN phase.
-template <int MODE, int CLS>
+// EX: exact-degree variants (min-sum kernels; the phi kernels sit at the register cap and keep the guarded buckets)
+template <int MODE, int CLS, bool EX>
 __device__ __forceinline__ float vn_cls(uint32_t msgb, uint32_t ce, int deg, int j4, int Z4, float llr, float clip) {
     if (CLS == 1) return vn_qc<32, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
     if (CLS == 2) return vn_qc<20, false, false, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    if (CLS == 3) return vn_qc<12, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    if (CLS == 4) return vn_qc<8, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    if (CLS == 5) return vn_qc<4, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
-    if (CLS == 6) return vn_qc<2, false, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
+    // exact-degree code (no guards) for every degree up to 12; deg is warp-uniform
+    if (CLS == 3) {
+        if (EX && deg == 9) return vn_qc<9, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (EX && deg == 10) return vn_qc<10, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (EX && deg == 11) return vn_qc<11, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        return vn_qc<12, false, true, MODE, EX>(msgb, ce, deg, j4, Z4, llr, clip);
+    }
+    if (CLS == 4) {
+        if (EX && deg == 5) return vn_qc<5, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (EX && deg == 6) return vn_qc<6, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        if (EX && deg == 7) return vn_qc<7, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        return vn_qc<8, false, true, MODE, EX>(msgb, ce, deg, j4, Z4, llr, clip);
+    }
+    if (CLS == 5) {
+        if (EX && deg == 3) return vn_qc<3, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        return vn_qc<4, false, true, MODE, EX>(msgb, ce, deg, j4, Z4, llr, clip);
+    }
+    if (CLS == 6) {
+        if (EX && deg == 1) return vn_qc<1, false, true, MODE, true>(msgb, ce, deg, j4, Z4, llr, clip);
+        return vn_qc<2, false, true, MODE, EX>(msgb, ce, deg, j4, Z4, llr, clip);
+    }
     if (CLS == 8) return vn_qc<12, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
     if (CLS == 9) return vn_qc<4, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
     if (CLS == 10) return vn_qc<1, true, true, MODE>(msgb, ce, deg, j4, Z4, llr, clip);
@@ -365,7 +396,7 @@ __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, fl
     }
 }
 
-template <int MODE, int CLS>
+template <int MODE, int CLS, bool EX>
 __device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
                                          const int4* s_col, uint32_t s_ce, int start, int end, float clip,
                                          bool final_pass, long long b) {
@@ -373,7 +404,7 @@ __device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, ui
         int4 ci = s_col[cc];
         if (w.lane_i < ci.z) {
             int v = ci.w + w.lane_i;
-            float x_tot = vn_cls<MODE, CLS>(msgb, s_ce + 8 * ci.x, ci.y, 4 * w.lane_i, 4 * p.Z, llr_s[v], clip);
+            float x_tot = vn_cls<MODE, CLS, EX>(msgb, s_ce + 8 * ci.x, ci.y, 4 * w.lane_i, 4 * p.Z, llr_s[v], clip);
             if (MODE == 0 && final_pass) {
                 int o = p.out_pos[v];
                 if (o >= 0) {
@@ -386,22 +417,22 @@ __device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, ui
     }
 }
 
-template <int MODE>
+template <int MODE, bool EX>
 __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
                                        const int4* s_col, uint32_t s_ce, float clip, bool final_pass,
                                        bool with_fused, long long b) {
     const int* ce = p.col_cls_end;
-    vn_class<MODE, 0>(p, w, msgb, llr_s, s_col, s_ce, 0, ce[0], clip, final_pass, b);
-    vn_class<MODE, 1>(p, w, msgb, llr_s, s_col, s_ce, ce[0], ce[1], clip, final_pass, b);
-    vn_class<MODE, 2>(p, w, msgb, llr_s, s_col, s_ce, ce[1], ce[2], clip, final_pass, b);
-    vn_class<MODE, 3>(p, w, msgb, llr_s, s_col, s_ce, ce[2], ce[3], clip, final_pass, b);
-    vn_class<MODE, 4>(p, w, msgb, llr_s, s_col, s_ce, ce[3], ce[4], clip, final_pass, b);
-    vn_class<MODE, 5>(p, w, msgb, llr_s, s_col, s_ce, ce[4], ce[5], clip, final_pass, b);
-    vn_class<MODE, 6>(p, w, msgb, llr_s, s_col, s_ce, ce[5], ce[6], clip, final_pass, b);
-    vn_class<MODE, 7>(p, w, msgb, llr_s, s_col, s_ce, ce[6], ce[7], clip, final_pass, b);
-    vn_class<MODE, 8>(p, w, msgb, llr_s, s_col, s_ce, ce[7], ce[8], clip, final_pass, b);
-    vn_class<MODE, 9>(p, w, msgb, llr_s, s_col, s_ce, ce[8], ce[9], clip, final_pass, b);
-    if (with_fused) vn_class<MODE, 10>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
+    vn_class<MODE, 0, EX>(p, w, msgb, llr_s, s_col, s_ce, 0, ce[0], clip, final_pass, b);
+    vn_class<MODE, 1, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[0], ce[1], clip, final_pass, b);
+    vn_class<MODE, 2, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[1], ce[2], clip, final_pass, b);
+    vn_class<MODE, 3, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[2], ce[3], clip, final_pass, b);
+    vn_class<MODE, 4, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[3], ce[4], clip, final_pass, b);
+    vn_class<MODE, 5, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[4], ce[5], clip, final_pass, b);
+    vn_class<MODE, 6, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[5], ce[6], clip, final_pass, b);
+    vn_class<MODE, 7, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[6], ce[7], clip, final_pass, b);
+    vn_class<MODE, 8, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[7], ce[8], clip, final_pass, b);
+    vn_class<MODE, 9, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[8], ce[9], clip, final_pass, b);
+    if (with_fused) vn_class<MODE, 10, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
 }
 
 template <int RULE>
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
         __syncthreads();
         if (tid == 0) *sat_flag = 0;
         // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
-        vn_all<1>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
+        vn_all<1, true>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
         __syncthreads();
         if (p.num_iter == 0) {
             for (int v = tid; v < N; v += T) {
@@ -492,7 +523,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
             cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag);
             __syncthreads();
             // ---- VN phase ---------------------------------------------------------------------------------------
-            vn_all<0>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
+            vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
             __syncthreads();
         }
         if (p.state_out) {
