@@ -9,7 +9,7 @@ SRCS = ["ldpc_bp_ref.c", "mapping_ref.c"]
 
 def build(force=False):
     srcs = [os.path.join(HERE, s) for s in SRCS]
-    deps = srcs + [os.path.join(HERE, "..", "sionna_b200", "csrc", "sb_math.h")]
+    deps = srcs + [os.path.join(HERE, "..", "sionna_b200", "csrc", h) for h in ("sb_math.h", "sb_logtab.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

@@ -47,11 +47,13 @@ static inline float m_log(float x, int mode) { return mode ? sb_logf(x) : logf(x
 static inline float m_tanh(float x, int mode) { return mode ? sb_tanhf(x) : tanhf(x); }
 static inline float m_atanh(float x, int mode) { return mode ? sb_atanhf(x) : atanhf(x); }
 
-/* decoding.py:1110-1120 */
+/* decoding.py:1110-1120. In kernel-math mode the two logs are the table-driven sb_logf_tab (sb_math.h), which is what
+ * the CUDA kernels evaluate inside phi. */
+static inline float m_log_phi(float x, int mode) { return mode ? sb_logf_tab(x) : logf(x); }
 static inline float phi(float x, int mode) {
     x = clipf(x, 8.5e-8f, 16.635532f);
     float t = m_exp(x, mode);
-    return m_log(t + 1.f, mode) - m_log(t - 1.f, mode);
+    return m_log_phi(t + 1.f, mode) - m_log_phi(t - 1.f, mode);
 }
 
 /* decoding.py:1126-1166. x: incoming v2c of one CN (deg values), out: c2v. */

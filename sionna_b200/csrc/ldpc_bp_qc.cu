@@ -45,6 +45,7 @@ struct QcParams {
     float* state_out;
     long long B;
     int num_iter, hard_out, use_tma;
+    int tab_rep;             // copies of the phi log table in shared memory (32 or 1; 0: rule does not use it)
     float offset, llr_max;
 };
 
@@ -66,7 +67,8 @@ struct QcParams {
 // SC = false: plain evaluation; one vote per check on its first edge pair probes for saturation and raises *sat_flag,
 // which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
 template <bool SC>
-__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag) {
+__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
+                                          const LogTab& lt) {
     const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
@@ -80,9 +82,9 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip,
         float a0 = __uint_as_float(b0 & 0x7fffffffu), a1 = __uint_as_float(b1 & 0x7fffffffu);
         float2 p = make_float2(0.f, 0.f);
         if (SC) {
-            if (!__all_sync(am, a0 >= SB_PHI_HI && a1 >= SB_PHI_HI)) p = sb_phif2(make_float2(a0, a1));   // (1)
+            if (!__all_sync(am, a0 >= SB_PHI_HI && a1 >= SB_PHI_HI)) p = sb_phif2(make_float2(a0, a1), lt);   // (1)
         } else {
-            p = sb_phif2(make_float2(a0, a1));
+            p = sb_phif2(make_float2(a0, a1), lt);
             if (l == 0 && __all_sync(am, a0 >= SB_PHI_HI && a1 >= SB_PHI_HI)) *sat_flag = 1;   // probe (benign race)
         }
         P = __fadd_rn(P, p.x);                            // :1150 sequential sum, ascending VN
@@ -96,7 +98,7 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip,
         par ^= b0;
         float a0 = __uint_as_float(b0 & 0x7fffffffu);
         float p = 0.f;
-        if (!SC || !__all_sync(am, a0 >= SB_PHI_HI)) p = sb_phif(a0);
+        if (!SC || !__all_sync(am, a0 >= SB_PHI_HI)) p = sb_phif_s(a0, lt);
         P = __fadd_rn(P, p);
         *q0 = __uint_as_float(__float_as_uint(p) | (b0 & 0x80000000u));
     }
@@ -111,13 +113,13 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip,
         unsigned b0 = __float_as_uint(*q0), b1 = __float_as_uint(*q1);
         float2 y;
         if (SC && __all_sync(am, ((b0 | b1) & 0x7fffffffu) == 0u)) {                                 // (2)
-            if (!have_yP) { yP = sb_phif(P); have_yP = true; }
+            if (!have_yP) { yP = sb_phif_s(P, lt); have_yP = true; }
             y = make_float2(yP, yP);
         } else {
             float2 m = __fadd2_rn(make_float2(__uint_as_float(b0 | 0x80000000u), __uint_as_float(b1 | 0x80000000u)),
                                   make_float2(P, P));     // (-p) + P  (:1155)
             if (SC && __all_sync(am, m.x <= SB_PHI_LO && m.y <= SB_PHI_LO)) y = make_float2(phi_max, phi_max);   // (3)
-            else y = sb_phif2(m);
+            else y = sb_phif2(m, lt);
         }
         *q0 = __uint_as_float(__float_as_uint(fminf(y.x, clip)) | ((b0 ^ par) & 0x80000000u));   // :1161-1163
         *q1 = __uint_as_float(__float_as_uint(fminf(y.y, clip)) | ((b1 ^ par) & 0x80000000u));
@@ -127,12 +129,12 @@ __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip,
         unsigned b0 = __float_as_uint(*q0);
         float y;
         if (SC && __all_sync(am, (b0 & 0x7fffffffu) == 0u)) {
-            if (!have_yP) { yP = sb_phif(P); have_yP = true; }
+            if (!have_yP) { yP = sb_phif_s(P, lt); have_yP = true; }
             y = yP;
         } else {
             float m = __fadd_rn(__uint_as_float(b0 | 0x80000000u), P);
             if (SC && __all_sync(am, m <= SB_PHI_LO)) y = phi_max;
-            else y = sb_phif(m);
+            else y = sb_phif_s(m, lt);
         }
         *q0 = __uint_as_float(__float_as_uint(fminf(y, clip)) | ((b0 ^ par) & 0x80000000u));
     }
@@ -217,10 +219,10 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
 
 template <int RULE, int CLS>
 __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset, float phi_max, bool sc,
-                                      int* sat_flag) {
+                                      int* sat_flag, const LogTab& lt) {
     if (RULE == SB_CN_BOXPLUS_PHI) {
-        if (sc) cn_phi_qc<true>(pm, Z, deg, clip, phi_max, sat_flag);
-        else cn_phi_qc<false>(pm, Z, deg, clip, phi_max, sat_flag);
+        if (sc) cn_phi_qc<true>(pm, Z, deg, clip, phi_max, sat_flag, lt);
+        else cn_phi_qc<false>(pm, Z, deg, clip, phi_max, sat_flag, lt);
     }
     else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
@@ -375,12 +377,12 @@ __device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx&
 template <int RULE, int CLS>
 __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
                                          const int4* s_row, int start, int end, float clip, bool fuse,
-                                         float phi_max, bool sc, int* sat_flag) {
+                                         float phi_max, bool sc, int* sat_flag, const LogTab& lt) {
     for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
         int4 ri = s_row[rr];
         if (w.lane_i < ri.z) {
             float* pm = msg + ri.x * p.Z + w.lane_i;
-            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag);
+            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt);
             if (fuse && ri.w >= 0) {
                 // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
                 // with a single incoming message) so the VN phase can skip the column
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     int2* s_ce_p = reinterpret_cast<int2*>(smem_raw + off_ce);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
     int* sat_flag = reinterpret_cast<int*>(smem_raw + off_bar + 8);
+    const int off_tab = off_bar + 16;                     // phi log table, tab_rep copies interleaved per entry
     const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
     const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
@@ -464,6 +467,20 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     for (int i = tid; i < p.n_cols; i += T) s_col[i] = p.col_info[i];
     for (int i = tid; i < p.n_rows; i += T) s_row[i] = p.row_info[i];
     for (int i = tid; i < p.nnz; i += T) s_ce_p[i] = p.col_edge[i];
+    LogTab lt;
+    lt.lane_base = 0; lt.rs = 0; lt.mask = 0;
+    if (RULE == SB_CN_BOXPLUS_PHI) {
+        // entry i, copy c at off_tab + (i * rep + c) * 8: with rep = 32 lane l reads copy l, i.e. bank pair l
+        const int rep = p.tab_rep;
+        float2* tab = reinterpret_cast<float2*>(smem_raw + off_tab);
+        for (int i = tid; i < SB_LOGTAB_N * rep; i += T) {
+            int e = i / rep;
+            tab[i] = make_float2(sb_logtab_dev[2 * e], sb_logtab_dev[2 * e + 1]);
+        }
+        lt.lane_base = smem_u32(smem_raw) + off_tab + (rep == 32 ? 8 * lane : 0);
+        lt.rs = rep == 32 ? SB_LOGTAB_SHIFT - 8 : SB_LOGTAB_SHIFT - 3;
+        lt.mask = (SB_LOGTAB_N - 1) << (rep == 32 ? 8 : 3);
+    }
     if (p.use_tma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -471,7 +488,7 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     __syncthreads();
 
     const float clip = p.llr_max;
-    const float phi_max = sb_phif(0.f);                   // phi at its lower clipping bound
+    const float phi_max = sb_phif(0.f);                   // phi at its lower clipping bound (global-memory table)
     uint32_t tma_phase = 0;
 
     for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -516,11 +533,11 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
             const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
             const int* re = p.row_cls_end;
-            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag);
-            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag);
-            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag);
-            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag);
-            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag);
+            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt);
             __syncthreads();
             // ---- VN phase ---------------------------------------------------------------------------------------
             vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
@@ -534,9 +551,9 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     }
 }
 
-size_t qc_smem_bytes(const sb_ldpc_graph* g) {
+size_t qc_smem_bytes(const sb_ldpc_graph* g, int tab_rep) {
     return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 16 +
-           (size_t)g->qc_nnz * 8 + 16 + 16;
+           (size_t)g->qc_nnz * 8 + 16 + 16 + (size_t)tab_rep * SB_LOGTAB_N * 8;
 }
 
 template <typename T>
@@ -702,9 +719,17 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
 // Test hook: evaluates phi on the device with the scalar (sb_math.h) and the packed (sb_math2.cuh) implementation.
 namespace {
 __global__ void debug_phi_kernel(const float* x, float* o1, float* o2, long long n) {
+    __shared__ float2 tab[SB_LOGTAB_N * 32];              // the 32-copy layout of the decoder
+    for (int i = threadIdx.x; i < SB_LOGTAB_N * 32; i += blockDim.x)
+        tab[i] = make_float2(sb_logtab_dev[2 * (i / 32)], sb_logtab_dev[2 * (i / 32) + 1]);
+    __syncthreads();
+    LogTab lt;
+    lt.lane_base = smem_u32(tab) + 8 * (threadIdx.x & 31);
+    lt.rs = SB_LOGTAB_SHIFT - 8;
+    lt.mask = (SB_LOGTAB_N - 1) << 8;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (2 * i + 1 < n) {
-        float2 r = sb_phif2(make_float2(x[2 * i], x[2 * i + 1]));
+        float2 r = sb_phif2(make_float2(x[2 * i], x[2 * i + 1]), lt);
         o2[2 * i] = r.x; o2[2 * i + 1] = r.y;
         o1[2 * i] = sb_phif(x[2 * i]); o1[2 * i + 1] = sb_phif(x[2 * i + 1]);
     }
@@ -725,7 +750,10 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
                      float* d_state_out, float* d_out, cudaStream_t stream, bool* handled) {
     *handled = false;
     if (!g->qc || !g->flooding || vn_rule != SB_VN_SUM || d_state_in || cn_rule > SB_CN_OFFSET_MINSUM) return SB_OK;
-    const size_t smem = qc_smem_bytes(g);
+    // boxplus-phi keeps the log table of phi in shared memory: one copy per bank pair if it fits, else a single copy
+    int tab_rep = cn_rule == SB_CN_BOXPLUS_PHI ? 32 : 0;
+    if (tab_rep && qc_smem_bytes(g, tab_rep) > (size_t)g->smem_optin) tab_rep = 1;
+    const size_t smem = qc_smem_bytes(g, tab_rep);
     if (smem > (size_t)g->smem_optin) return SB_OK;
     if ((cn_rule == SB_CN_MINSUM || cn_rule == SB_CN_OFFSET_MINSUM) &&
         !(llr_max < 100000.f && (float)(g->qc_max_row_deg - 1) * llr_max < 99000.f))
@@ -741,7 +769,7 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     p.col_edge = (const int2*)g->d_qc_col_edge; p.in_idx = g->d_qc_in_idx; p.out_pos = g->d_qc_out_pos;
     p.slot_of_edge = g->d_qc_slot_of_edge;
     p.llr = d_llr; p.out = d_out; p.state_out = d_state_out; p.B = batch; p.num_iter = num_iter; p.hard_out = hard_out;
-    p.offset = offset; p.llr_max = llr_max;
+    p.offset = offset; p.llr_max = llr_max; p.tab_rep = tab_rep;
     p.use_tma = (g->n_in % 4 == 0) && (g->n_in <= p.E_alloc) && ((reinterpret_cast<uintptr_t>(d_llr) & 15) == 0);
     const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
     int groups = std::max(1, std::min(24 / Zb, std::max(g->qc_rows, g->qc_cols)));

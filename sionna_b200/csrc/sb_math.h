@@ -17,6 +17,7 @@
 //   sb_expf(8.5e-8f) == 1+2^-23   and   sb_logf(2^24) == sb_logf(2^24-1).
 #pragma once
 #include <stdint.h>
+#include "sb_logtab.h"
 
 #if defined(__CUDA_ARCH__)
 #define SB_HD __host__ __device__ __forceinline__
@@ -99,13 +100,52 @@ SB_HD float sb_logf(float y) {
     return SB_FMA(ef, 0.693145751953125f, t2);             // ... one rounding for e*ln2_hi + t2
 }
 
+// Table-driven log(y) for positive normal y, used by phi (two logs per phi, two phi per edge per iteration: the hot
+// spot of the boxplus-phi decoder). y = 2^e m, m in [sqrt(.5), sqrt(2)) as in sb_logf; the 64-entry table
+// (sb_logtab.h, tools/gen_logtab.py) gives {1/c, log c} for the piece of m, r = m/c - 1 (one FMA, |r| < 0.008) and
+// log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation < 1e-11). 8 floating-point operations instead of 16.
+// `tab` points at SB_LOGTAB_N {inv_c, logc} pairs; `stride` is the distance between pairs in floats (the QC decoder
+// keeps one copy per shared-memory bank pair, see ldpc_bp_qc.cu).
+#if defined(__CUDACC__)
+static __device__ const float sb_logtab_dev[2 * SB_LOGTAB_N] = {SB_LOGTAB_VALUES};
+#endif
+static const float sb_logtab_host[2 * SB_LOGTAB_N] = {SB_LOGTAB_VALUES};
+#if defined(__CUDA_ARCH__)
+#define SB_LOGTAB_DEFAULT sb_logtab_dev
+#else
+#define SB_LOGTAB_DEFAULT sb_logtab_host
+#endif
+
+SB_HD float sb_logf_tab_core(float y, float inv_c, float logc, int32_t e, int32_t ix) {
+    float m = SB_I2F(ix - (e << 23));
+    float ef = (float)e;
+    float r = SB_FMA(m, inv_c, -1.0f);
+    float q = SB_FMA(r, -0.25f, 0x1.555556p-2f);
+    q = SB_FMA(q, r, -0.5f);
+    float r2 = SB_MUL(r, r);
+    float s = SB_FMA(r2, q, r);
+    float lo = SB_FMA(ef, 1.42860677e-06f, s);
+    float t2 = SB_ADD(logc, lo);
+    (void)y;
+    return SB_FMA(ef, 0.693145751953125f, t2);
+}
+
+SB_HD float sb_logf_tab(float y) {
+    int32_t ix = SB_F2I(y);
+    int32_t k = ix - 0x3f3504f3;
+    int32_t e = k >> 23;
+    int32_t i = (k >> SB_LOGTAB_SHIFT) & (SB_LOGTAB_N - 1);
+    const float* tab = SB_LOGTAB_DEFAULT;
+    return sb_logf_tab_core(y, tab[2 * i], tab[2 * i + 1], e, ix);
+}
+
 // phi(x) = log(e^x + 1) - log(e^x - 1) with the reference's fp32 clipping constants
 // (/root/reference/src/sionna/phy/fec/ldpc/decoding.py:1110-1120).
 SB_HD float sb_phif(float x) {
     x = x < 8.5e-8f ? 8.5e-8f : x;
     x = x > 16.635532f ? 16.635532f : x;
     float t = sb_expf(x);
-    return SB_SUB(sb_logf(SB_ADD(t, 1.0f)), sb_logf(SB_SUB(t, 1.0f)));
+    return SB_SUB(sb_logf_tab(SB_ADD(t, 1.0f)), sb_logf_tab(SB_SUB(t, 1.0f)));
 }
 
 // tanh(z): odd; |z| < 2^-12 -> z (exact to fp32), else (1-q)/(1+q), q = e^{-2|z|}

@@ -39,6 +39,28 @@ int main(void) {
            worst_exp, wx, worst_log, wl, worst_tanh, wt, worst_atanh, wa);
     float x = 8.5e-8f; printf("exp(8.5e-8)=%a  phi(0)=%.9g phi(8.5e-8)=%.9g phi(1)=%.9g phi(10)=%.9g phi(16)=%.9g phi(16.635532)=%.9g phi(40)=%.9g\n",
         sb_expf(x), sb_phif(0.f), sb_phif(x), sb_phif(1.f), sb_phif(10.f), sb_phif(16.f), sb_phif(16.635532f), sb_phif(40.f));
+    {   // table log used inside phi: accuracy on all positive normals, and phi >= 0 / monotone on its whole domain
+        double wl2 = 0; float xl2 = 0; long long neg = 0, nonmono = 0; float xneg = 0;
+        #pragma omp parallel
+        {
+            double w_ = 0; float x_ = 0; long long ng = 0, nm = 0; float xn = 0;
+            #pragma omp for schedule(static)
+            for (long long i = 0x00800000LL; i < 0x7f800000LL; ++i) {
+                uint32_t u = (uint32_t)i; float y; memcpy(&y, &u, 4);
+                double ref = log((double)y); double err = fabs((double)sb_logf_tab(y) - ref) / ulp_of(ref);
+                if (err > w_) { w_ = err; x_ = y; }
+                if (y >= 8.5e-8f && y <= 16.635532f) {
+                    float ph = sb_phif(y);
+                    if (ph < 0.f || (ph == 0.f && signbit(ph))) { ++ng; xn = y; }
+                    uint32_t u2 = u + 1; float y2; memcpy(&y2, &u2, 4);
+                    if (y2 <= 16.635532f && sb_phif(y2) > ph) ++nm;
+                }
+            }
+            #pragma omp critical
+            { if (w_ > wl2) { wl2 = w_; xl2 = x_; } neg += ng; nonmono += nm; if (ng) xneg = xn; }
+        }
+        printf("logf_tab max ulp err %.4f at %a; phi<0 count %lld (last at %a); phi non-monotone steps %lld\n", wl2, xl2, neg, xneg, nonmono);
+    }
     printf("log(2^24)=%a log(2^24-1)=%a phi(2*phi(0))=%g\n", sb_logf(16777216.f), sb_logf(16777215.f), sb_phif(2*sb_phif(0.f)));
     return 0;
 }
