@@ -66,9 +66,9 @@ struct QcParams {
 #define SB_PHI_LO 8.5e-8f
 // SC = false: plain evaluation; one vote per check on its first edge pair probes for saturation and raises *sat_flag,
 // which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
-template <bool SC>
+template <bool SC, class LT>
 __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
-                                          const LogTab& lt) {
+                                          const LT& lt) {
     const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
@@ -217,12 +217,12 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
     }
 }
 
-template <int RULE, int CLS>
+template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset, float phi_max, bool sc,
-                                      int* sat_flag, const LogTab& lt) {
+                                      int* sat_flag, const LT& lt) {
     if (RULE == SB_CN_BOXPLUS_PHI) {
-        if (sc) cn_phi_qc<true>(pm, Z, deg, clip, phi_max, sat_flag, lt);
-        else cn_phi_qc<false>(pm, Z, deg, clip, phi_max, sat_flag, lt);
+        if (sc) cn_phi_qc<true, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
+        else cn_phi_qc<false, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
     }
     else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
@@ -374,15 +374,15 @@ __device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx&
     return start + (w.grp - start_mod + (w.grp < start_mod ? w.G : 0));
 }
 
-template <int RULE, int CLS>
+template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
                                          const int4* s_row, int start, int end, float clip, bool fuse,
-                                         float phi_max, bool sc, int* sat_flag, const LogTab& lt) {
+                                         float phi_max, bool sc, int* sat_flag, const LT& lt) {
     for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
         int4 ri = s_row[rr];
         if (w.lane_i < ri.z) {
             float* pm = msg + ri.x * p.Z + w.lane_i;
-            cn_qc<RULE, CLS>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt);
+            cn_qc<RULE, CLS, LT>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt);
             if (fuse && ri.w >= 0) {
                 // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
                 // with a single incoming message) so the VN phase can skip the column
@@ -437,7 +437,7 @@ __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint
     if (with_fused) vn_class<MODE, 10, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
 }
 
-template <int RULE>
+template <int RULE, int REP>                              // REP: copies of the phi log table (32 or 1)
 __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -467,19 +467,17 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
     for (int i = tid; i < p.n_cols; i += T) s_col[i] = p.col_info[i];
     for (int i = tid; i < p.n_rows; i += T) s_row[i] = p.row_info[i];
     for (int i = tid; i < p.nnz; i += T) s_ce_p[i] = p.col_edge[i];
-    LogTab lt;
-    lt.lane_base = 0; lt.rs = 0; lt.mask = 0;
+    LogTab<REP> lt;
+    lt.inv = 0; lt.lane_off = 0;
     if (RULE == SB_CN_BOXPLUS_PHI) {
-        // entry i, copy c at off_tab + (i * rep + c) * 8: with rep = 32 lane l reads copy l, i.e. bank pair l
-        const int rep = p.tab_rep;
-        float2* tab = reinterpret_cast<float2*>(smem_raw + off_tab);
-        for (int i = tid; i < SB_LOGTAB_N * rep; i += T) {
-            int e = i / rep;
-            tab[i] = make_float2(sb_logtab_dev[2 * e], sb_logtab_dev[2 * e + 1]);
+        // two arrays of SB_LOGTAB_N * REP floats; entry i, copy c at (i * REP + c) * 4: with REP = 32 lane l reads bank l
+        float* tab = reinterpret_cast<float*>(smem_raw + off_tab);
+        for (int i = tid; i < SB_LOGTAB_N * REP; i += T) {
+            tab[i] = sb_logtab_dev[2 * (i / REP)];
+            tab[SB_LOGTAB_N * REP + i] = sb_logtab_dev[2 * (i / REP) + 1];
         }
-        lt.lane_base = smem_u32(smem_raw) + off_tab + (rep == 32 ? 8 * lane : 0);
-        lt.rs = rep == 32 ? SB_LOGTAB_SHIFT - 8 : SB_LOGTAB_SHIFT - 3;
-        lt.mask = (SB_LOGTAB_N - 1) << (rep == 32 ? 8 : 3);
+        lt.inv = msgb + off_tab;
+        lt.lane_off = REP == 32 ? 4 * lane : 0;
     }
     if (p.use_tma && tid == 0) {
         mbar_init(bar, 1);
@@ -533,11 +531,11 @@ __global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constan
             const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
             const int* re = p.row_cls_end;
-            cn_class<RULE, 0>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 1>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 2>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 3>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 4>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 2, LogTab<REP>>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 3, LogTab<REP>>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 4, LogTab<REP>>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt);
             __syncthreads();
             // ---- VN phase ---------------------------------------------------------------------------------------
             vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
@@ -578,7 +576,7 @@ int qc_ensure_uploaded(sb_ldpc_graph* g) {
 
 template <int RULE>
 int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = ldpc_bp_qc_kernel<RULE>;
+    auto kern = (RULE == SB_CN_BOXPLUS_PHI && p.tab_rep == 1) ? ldpc_bp_qc_kernel<RULE, 1> : ldpc_bp_qc_kernel<RULE, 32>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -719,14 +717,15 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
 // Test hook: evaluates phi on the device with the scalar (sb_math.h) and the packed (sb_math2.cuh) implementation.
 namespace {
 __global__ void debug_phi_kernel(const float* x, float* o1, float* o2, long long n) {
-    __shared__ float2 tab[SB_LOGTAB_N * 32];              // the 32-copy layout of the decoder
-    for (int i = threadIdx.x; i < SB_LOGTAB_N * 32; i += blockDim.x)
-        tab[i] = make_float2(sb_logtab_dev[2 * (i / 32)], sb_logtab_dev[2 * (i / 32) + 1]);
+    __shared__ float tab[2 * SB_LOGTAB_N * 32];           // the 32-copy layout of the decoder
+    for (int i = threadIdx.x; i < SB_LOGTAB_N * 32; i += blockDim.x) {
+        tab[i] = sb_logtab_dev[2 * (i / 32)];
+        tab[SB_LOGTAB_N * 32 + i] = sb_logtab_dev[2 * (i / 32) + 1];
+    }
     __syncthreads();
-    LogTab lt;
-    lt.lane_base = smem_u32(tab) + 8 * (threadIdx.x & 31);
-    lt.rs = SB_LOGTAB_SHIFT - 8;
-    lt.mask = (SB_LOGTAB_N - 1) << 8;
+    LogTab<32> lt;
+    lt.inv = smem_u32(tab);
+    lt.lane_off = 4 * (threadIdx.x & 31);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (2 * i + 1 < n) {
         float2 r = sb_phif2(make_float2(x[2 * i], x[2 * i + 1]), lt);

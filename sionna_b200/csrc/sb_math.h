@@ -100,12 +100,13 @@ SB_HD float sb_logf(float y) {
     return SB_FMA(ef, 0.693145751953125f, t2);             // ... one rounding for e*ln2_hi + t2
 }
 
-// Table-driven log(y) for positive normal y, used by phi (two logs per phi, two phi per edge per iteration: the hot
-// spot of the boxplus-phi decoder). y = 2^e m, m in [sqrt(.5), sqrt(2)) as in sb_logf; the 64-entry table
-// (sb_logtab.h, tools/gen_logtab.py) gives {1/c, log c} for the piece of m, r = m/c - 1 (one FMA, |r| < 0.008) and
-// log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation < 1e-11). 8 floating-point operations instead of 16.
-// `tab` points at SB_LOGTAB_N {inv_c, logc} pairs; `stride` is the distance between pairs in floats (the QC decoder
-// keeps one copy per shared-memory bank pair, see ldpc_bp_qc.cu).
+// Table-driven log(y) for positive normal y, used by phi only (two logs per phi, two phi per edge per iteration: the
+// hot spot of the boxplus-phi decoder). y = 2^(E-127) m, m in [1, 2) straight from the bit fields; the 64-entry table
+// (sb_logtab.h, tools/gen_logtab.py) gives {1/c, log c} for the piece of m, r = m/c - 1 (one FMA, |r| <= 1/64) and
+// log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation < 2e-10). E-127 is obtained as a float without a conversion:
+// float(0x4B400000 | E) = 12582912 + E exactly. 9 floating-point and 5 integer operations (sb_logf: 16 + 5 + I2F).
+// Accuracy (tools/check_math.c, exhaustive): <= 1 ulp for y >= 1; for y < 1 the absolute error stays <= 6e-8 (the
+// result is not relatively accurate just below 1, which phi does not need: log(t-1) ~ 0 is subtracted from log(t+1) ~ 1).
 #if defined(__CUDACC__)
 static __device__ const float sb_logtab_dev[2 * SB_LOGTAB_N] = {SB_LOGTAB_VALUES};
 #endif
@@ -116,9 +117,9 @@ static const float sb_logtab_host[2 * SB_LOGTAB_N] = {SB_LOGTAB_VALUES};
 #define SB_LOGTAB_DEFAULT sb_logtab_host
 #endif
 
-SB_HD float sb_logf_tab_core(float y, float inv_c, float logc, int32_t e, int32_t ix) {
-    float m = SB_I2F(ix - (e << 23));
-    float ef = (float)e;
+SB_HD float sb_logf_tab_core(int32_t ix, float inv_c, float logc) {
+    float m = SB_I2F((ix & 0x007fffff) | 0x3f800000);
+    float ef = SB_ADD(SB_I2F((int32_t)((uint32_t)ix >> 23) | 0x4B400000), -12583039.0f);   // E - 127, exact
     float r = SB_FMA(m, inv_c, -1.0f);
     float q = SB_FMA(r, -0.25f, 0x1.555556p-2f);
     q = SB_FMA(q, r, -0.5f);
@@ -126,17 +127,14 @@ SB_HD float sb_logf_tab_core(float y, float inv_c, float logc, int32_t e, int32_
     float s = SB_FMA(r2, q, r);
     float lo = SB_FMA(ef, 1.42860677e-06f, s);
     float t2 = SB_ADD(logc, lo);
-    (void)y;
     return SB_FMA(ef, 0.693145751953125f, t2);
 }
 
 SB_HD float sb_logf_tab(float y) {
     int32_t ix = SB_F2I(y);
-    int32_t k = ix - 0x3f3504f3;
-    int32_t e = k >> 23;
-    int32_t i = (k >> SB_LOGTAB_SHIFT) & (SB_LOGTAB_N - 1);
+    int32_t i = (ix >> SB_LOGTAB_SHIFT) & (SB_LOGTAB_N - 1);
     const float* tab = SB_LOGTAB_DEFAULT;
-    return sb_logf_tab_core(y, tab[2 * i], tab[2 * i + 1], e, ix);
+    return sb_logf_tab_core(ix, tab[2 * i], tab[2 * i + 1]);
 }
 
 // phi(x) = log(e^x + 1) - log(e^x - 1) with the reference's fp32 clipping constants

@@ -55,58 +55,74 @@ __device__ __forceinline__ float2 sb_logf2(float2 y) {
     return __ffma2_rn(ef, f2s(0.693145751953125f), t2);
 }
 
-// Shared-memory copy of the sb_logf_tab table (sb_math.h). `lane_base` is the 32-bit shared-window address of this
-// lane's copy of entry 0; entry i sits at lane_base + ((k >> rs) & mask) with k = bits(y) - 0x3f3504f3, i.e. the host
-// picks rs/mask for the replication factor: 32 copies (one per bank pair, conflict-free LDS.64: rs 9, mask 0x3f00,
-// lane offset 8*lane) when the table fits next to the messages, else a single copy (rs 14, mask 0x1f8).
+// Shared-memory copy of the sb_logf_tab table (sb_math.h), split into an inv_c array and a log c array so that the
+// packed code loads each operand straight into its register pair. Entry i of this lane's copy sits at offset
+// ((bits(y) >> rs) & mask) | lane_off of either array: the host picks the replication factor -- 32 copies (one per bank,
+// conflict-free LDS: rs 10, mask 0x1f80, lane_off 4*lane) when the table fits next to the messages, else a single copy
+// (rs 15, mask 0xfc, lane_off 0).
+template <int REP>                                        // REP = 32 or 1: compile-time shift, mask and array distance
 struct LogTab {
-    uint32_t lane_base;
-    int rs, mask;
+    uint32_t inv, lane_off;                               // `inv` is CTA-uniform; the log c array follows the inv_c array
+    static constexpr int rs = REP == 32 ? SB_LOGTAB_SHIFT - 7 : SB_LOGTAB_SHIFT - 2;
+    static constexpr int mask = (SB_LOGTAB_N - 1) << (REP == 32 ? 7 : 2);
+    static constexpr int dist = SB_LOGTAB_N * REP * 4;
 };
 
-__device__ __forceinline__ float2 lds_f2(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+// (a & MASK) | c in one LOP3 (c in a register; nvcc otherwise emits two LOP3 when both constants are immediates)
+template <int MASK>
+__device__ __forceinline__ int and_or(int a, int c) {
+    int d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(MASK), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ float lds_ro(uint32_t a) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));     // read-only after the prologue barrier
     return v;
 }
 
 // sb_logf_tab, two at a time (same operation sequence per element)
-__device__ __forceinline__ float2 sb_logf2_tab(float2 y, const LogTab& lt) {
+template <class LT>
+__device__ __forceinline__ float2 sb_logf2_tab(float2 y, const LT& lt) {
     int ix0 = f2i_mov(y.x), ix1 = f2i_mov(y.y);
-    int k0 = ix0 - 0x3f3504f3, k1 = ix1 - 0x3f3504f3;
-    float2 T0 = lds_f2(lt.lane_base + ((k0 >> lt.rs) & lt.mask));
-    float2 T1 = lds_f2(lt.lane_base + ((k1 >> lt.rs) & lt.mask));
-    int e0 = k0 >> 23, e1 = k1 >> 23;
-    float2 m = f2(i2f_mov(ix0 - (e0 << 23)), i2f_mov(ix1 - (e1 << 23)));
-    float2 ef = f2((float)e0, (float)e1);
-    float2 r = __ffma2_rn(m, f2(T0.x, T1.x), f2s(-1.0f));
+    uint32_t o0 = lt.inv + (((ix0 >> LT::rs) & LT::mask) | lt.lane_off);
+    uint32_t o1 = lt.inv + (((ix1 >> LT::rs) & LT::mask) | lt.lane_off);
+    float2 inv_c = f2(lds_ro(o0), lds_ro(o1));
+    float2 logc = f2(lds_ro(o0 + LT::dist), lds_ro(o1 + LT::dist));
+    float2 m = f2(i2f_mov(and_or<0x007fffff>(ix0, 0x3f800000)), i2f_mov(and_or<0x007fffff>(ix1, 0x3f800000)));
+    float2 F = f2(i2f_mov((int)((unsigned)ix0 >> 23) | 0x4B400000), i2f_mov((int)((unsigned)ix1 >> 23) | 0x4B400000));
+    float2 ef = __fadd2_rn(F, f2s(-12583039.0f));
+    float2 r = __ffma2_rn(m, inv_c, f2s(-1.0f));
     float2 q = __ffma2_rn(r, f2s(-0.25f), f2s(0x1.555556p-2f));
     q = __ffma2_rn(q, r, f2s(-0.5f));
     float2 r2 = __fmul2_rn(r, r);
     float2 s = __ffma2_rn(r2, q, r);
     float2 lo = __ffma2_rn(ef, f2s(1.42860677e-06f), s);
-    float2 t2 = __fadd2_rn(f2(T0.y, T1.y), lo);
+    float2 t2 = __fadd2_rn(logc, lo);
     return __ffma2_rn(ef, f2s(0.693145751953125f), t2);
 }
 
-__device__ __forceinline__ float sb_logf_tab_s(float y, const LogTab& lt) {
+template <class LT>
+__device__ __forceinline__ float sb_logf_tab_s(float y, const LT& lt) {
     int ix = __float_as_int(y);
-    int k = ix - 0x3f3504f3;
-    float2 T = lds_f2(lt.lane_base + ((k >> lt.rs) & lt.mask));
-    return sb_logf_tab_core(y, T.x, T.y, k >> 23, ix);
+    uint32_t o = lt.inv + (((ix >> LT::rs) & LT::mask) | lt.lane_off);
+    return sb_logf_tab_core(ix, lds_ro(o), lds_ro(o + LT::dist));
 }
 
 // phi(x) = log(e^x + 1) - log(e^x - 1) with the reference's fp32 clipping (see sb_phif)
-__device__ __forceinline__ float2 sb_phif2(float2 x, const LogTab& lt) {
+template <class LT>
+__device__ __forceinline__ float2 sb_phif2(float2 x, const LT& lt) {
     x.x = fminf(fmaxf(x.x, 8.5e-8f), 16.635532f);
     x.y = fminf(fmaxf(x.y, 8.5e-8f), 16.635532f);
     float2 t = sb_expf2_inrange(x);
-    float2 la = sb_logf2_tab(f2(__fadd_rn(t.x, 1.0f), __fadd_rn(t.y, 1.0f)), lt);
-    float2 lb = sb_logf2_tab(f2(__fadd_rn(t.x, -1.0f), __fadd_rn(t.y, -1.0f)), lt);
+    float2 la = sb_logf2_tab(__fadd2_rn(t, f2s(1.0f)), lt);
+    float2 lb = sb_logf2_tab(__fadd2_rn(t, f2s(-1.0f)), lt);
     return __ffma2_rn(lb, f2s(-1.0f), la);                   // la - lb, one rounding
 }
 
-__device__ __forceinline__ float sb_phif_s(float x, const LogTab& lt) {
+template <class LT>
+__device__ __forceinline__ float sb_phif_s(float x, const LT& lt) {
     x = fminf(fmaxf(x, 8.5e-8f), 16.635532f);
     float t = sb_expf(x);
     return __fsub_rn(sb_logf_tab_s(__fadd_rn(t, 1.0f), lt), sb_logf_tab_s(__fadd_rn(t, -1.0f), lt));
