@@ -65,3 +65,49 @@ def calculate_tb_size(modulation_order, target_coderate, target_tb_size=None, nu
     len_first = q * int(np.floor(num_coded_bits / (q * num_cb)))
     cw_length = np.array([len_first] * num_first + [len_last] * num_last, np.int64)
     return tb_size, cb_size, num_cb, tb_crc_length, cb_crc_length, cw_length
+
+
+_NR_TABLES = None
+
+
+def nr_tables():
+    """3GPP table data (MCS tables, PUSCH codebooks) of codes/nr_tables.npz (tools/make_nr_tables.py)."""
+    global _NR_TABLES
+    if _NR_TABLES is None:
+        import os
+        with np.load(os.path.join(os.path.dirname(__file__), "codes", "nr_tables.npz")) as z:
+            _NR_TABLES = {k: z[k] for k in z.files}
+    return _NR_TABLES
+
+
+def decode_mcs_index(mcs_index, table_index=1, is_pusch=True, transform_precoding=False, pi2bpsk=False,
+                     check_index_validity=True, verbose=False):
+    """(modulation_order, target_coderate) of an MCS index (utils.py:80-304). Table set: TS 38.214 5.1.3.1-1..4 for
+    PDSCH and for PUSCH without transform precoding, 6.1.4.1-1/2 for PUSCH with transform precoding (where the first
+    entries scale with q = 1 (pi/2-BPSK) or 2). Accepts scalars or arrays (broadcast together); rates are /1024."""
+    idx = np.asarray(mcs_index)
+    shape = np.broadcast(idx, np.asarray(table_index), np.asarray(is_pusch), np.asarray(transform_precoding),
+                         np.asarray(pi2bpsk)).shape
+    mcs = np.broadcast_to(idx, shape).astype(np.int64)
+    tab = np.broadcast_to(np.asarray(table_index), shape).astype(np.int64)
+    pus = np.broadcast_to(np.asarray(is_pusch, bool), shape)
+    tpr = np.broadcast_to(np.asarray(transform_precoding, bool), shape)
+    q = np.where(np.broadcast_to(np.asarray(pi2bpsk, bool), shape), 1, 2)
+    assert np.all(mcs >= 0), "mcs_index must be non-negative"
+    assert np.all(mcs <= 28), "mcs_index must be <= 28"
+    assert np.all(np.isin(tab, (1, 2, 3, 4))), "table_index must contain values in [1,2,3,4]"
+    t = nr_tables()
+    family = np.where(~pus | ~tpr, 1, 0)                      # 0: PUSCH with transform precoding
+    mod = t["mcs_mod_orders"][family, tab - 1, mcs].astype(np.int64)
+    rate = t["mcs_target_rates"][family, tab - 1, mcs].astype(np.float64)
+    if check_index_validity:
+        assert np.all(mod >= 0), "Invalid MCS index"
+    scaled = (family == 0) & (((tab == 1) & (mcs < 2)) | ((tab == 2) & (mcs < 6)))
+    mod = np.where(scaled, mod * q, mod)
+    rate = np.where(scaled, rate / q, rate) / 1024
+    if verbose:
+        print(f"Modulation order: {mod}")
+        print(f"Target code rate: {rate}")
+    if shape == ():
+        return int(mod), np.float32(rate)
+    return mod.astype(np.int32), rate.astype(np.float32)
