@@ -200,6 +200,17 @@ int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, 
 int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
                           int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_re,
                           int32_t add_noise, uint64_t seed, uint64_t offset, void* stream);
+/* PUSCHPrecoder.call (nr/pusch_precoder.py:75-95): d_x [batch, num_tx, num_layers, num_re] complex, d_w [num_tx,
+ * num_ports, num_layers] complex -> d_y [batch, num_tx, num_ports, num_re], y = W x per resource element. */
+int sb_pusch_precode(const float* d_x, const float* d_w, float* d_y, int64_t batch, int32_t num_tx, int32_t num_layers,
+                     int32_t num_ports, int64_t num_re, void* stream);
+/* PUSCHLSChannelEstimator.estimate_at_pilot_locations (nr/pusch_channel_estimation.py:117-169), the part after the LS
+ * division (sb_ls_at_pilots): in-place CDM de-spreading of d_h [rows, num_pilots] complex (pilots ordered DMRS symbol
+ * major): average over the two symbols of a double-symbol DMRS, then sum / 2 over groups of group_size = 2 *
+ * num_cdm_groups_without_data adjacent pilots, written back to the group's non-zero entries; d_err_var [rows,
+ * num_pilots] is scaled by 1/2 (and by another 1/2 for double-symbol DMRS). */
+int sb_pusch_ls_combine(float* d_h, float* d_err_var, int64_t rows, int32_t num_pilots, int32_t pilots_per_dmrs_symbol,
+                        int32_t dmrs_length, int32_t group_size, void* stream);
 /* lmmse_equalizer (mimo/equalization.py:101-233, whiten_interference=True): d_y [num, M], d_h [num, M, K], d_s [num, M, M]
  * -> d_x_hat [num, K] complex, d_no_eff [num, K] real. 1 <= K <= 16, K <= M. */
 int sb_lmmse_equalize(const float* d_y, const float* d_h, const float* d_s, float* d_x_hat, float* d_no_eff, int64_t num,

@@ -107,3 +107,58 @@ def tb_encode(u, num_coded_bits, target_coderate, m, num_layers, n_rnti, n_id, s
     if scramble:
         c = np.abs(c - generate_prng_seq(sum(cw), n_rnti * 2 ** 15 + n_id))
     return c.astype(np.float32)
+
+
+# ---- PUSCH (SURVEY.md 8(f2)) -----------------------------------------------------------------------------------------
+def layer_map(x, num_layers):
+    """[..., n] -> [..., num_layers, n / num_layers], symbol i to layer i mod num_layers (layer_mapping.py:176-181,199)."""
+    n = x.shape[-1]
+    return np.swapaxes(x.reshape(x.shape[:-1] + (n // num_layers, num_layers)), -1, -2)
+
+
+def layer_demap(llr, num_bits_per_symbol):
+    """[..., num_layers, n] -> [..., num_layers * n] keeping the LLRs of a symbol together (layer_mapping.py:268-280)."""
+    q = num_bits_per_symbol
+    x = llr.reshape(llr.shape[:-1] + (llr.shape[-1] // q, q))
+    return np.swapaxes(x, -2, -3).reshape(llr.shape[:-2] + (-1,))
+
+
+def pusch_transmit(cfg, b, tb_size, num_coded_bits):
+    """Frequency-domain PUSCH slot of ONE transmitter (pusch_transmitter.py:199-243): b [B, tb_size] ->
+    [B, num_antenna_ports, num_symbols, num_subcarriers].
+
+    `cfg` carries host-side configuration results only: m (bits/symbol), target_coderate, num_layers, n_rnti, n_id,
+    dmrs_mask [subcarriers, symbols] and dmrs_grid [layers, subcarriers, symbols] restricted to the allocation, and the
+    precoding matrix w [ports, layers] or None."""
+    from . import mapping as M
+    c = tb_encode(b, num_coded_bits, cfg["target_coderate"], cfg["m"], cfg["num_layers"], cfg["n_rnti"], cfg["n_id"])
+    x = M.mapper(c, M.qam(cfg["m"]))[0]                                # [B, symbols] (second output: symbol indices)
+    xl = layer_map(x, cfg["num_layers"])                               # [B, L, n]
+    mask = np.asarray(cfg["dmrs_mask"]).T                              # [S, F]
+    dm = np.transpose(np.asarray(cfg["dmrs_grid"]), (0, 2, 1))         # [L, S, F]
+    bsz, nl = xl.shape[0], cfg["num_layers"]
+    grid = np.zeros((bsz, nl) + mask.shape, complex)
+    for l in range(nl):                                                # resource_grid.py:394-412: row-major fill
+        grid[:, l][:, ~mask] = xl[:, l]
+        grid[:, l][:, mask] = dm[l][mask]
+    if cfg.get("w") is not None:                                       # pusch_precoder.py:75-95
+        grid = np.einsum("pl,blsf->bpsf", np.asarray(cfg["w"]), grid)
+    return grid
+
+
+def pusch_ls_combine(h, err, num_dmrs_syms, dmrs_length, num_cdm_groups_without_data):
+    """CDM de-spreading of the LS estimates h [..., P] at the DMRS REs (pusch_channel_estimation.py:138-169)."""
+    shp = h.shape
+    pps = shp[-1] // num_dmrs_syms
+    h = h.reshape(shp[:-1] + (num_dmrs_syms, pps))
+    err = np.array(err, dtype=float)
+    if dmrs_length == 2:
+        h = (h[..., 0::2, :] + h[..., 1::2, :]) / 2
+        h = np.repeat(h, 2, axis=-2)
+        err = err / 2
+    n = 2 * num_cdm_groups_without_data
+    h = h.reshape(shp[:-1] + (shp[-1] // n, n))
+    cond = np.abs(h) > 0
+    avg = np.sum(h, axis=-1, keepdims=True) / 2
+    h = np.where(cond, np.repeat(avg, n, axis=-1), 0)
+    return h.reshape(shp), err / 2

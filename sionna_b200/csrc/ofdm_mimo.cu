@@ -8,6 +8,8 @@
 //   sb_ls_at_pilots       BaseChannelEstimator.call pilot gather :138-150 + LSChannelEstimator :257-285
 //   sb_interp_lin         LinearInterpolator._interpolate ofdm/channel_estimation.py:657-734
 //   sb_apply_ofdm_channel ApplyOFDMChannel.call    channel/apply_ofdm_channel.py:70-80
+//   sb_pusch_precode      PUSCHPrecoder.call       nr/pusch_precoder.py:75-95
+//   sb_pusch_ls_combine   PUSCHLSChannelEstimator.estimate_at_pilot_locations   nr/pusch_channel_estimation.py:117-169
 //   sb_lmmse_equalize     lmmse_equalizer mimo/equalization.py:101-233 (+ whiten_channel mimo/utils.py:292-357,
 //                         lmmse_matrix :11-99)
 //   sb_ofdm_lmmse         OFDMEqualizer.call ofdm/equalization.py:109-275 with the LMMSE equaliser fused in: the
@@ -570,6 +572,101 @@ extern "C" int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const f
     apply_ofdm_channel_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const float2*)d_x, (const float2*)d_h, d_no, no_inner > 0 ? no_inner : 1, (float2*)d_y, batch, num_rx_ant_total,
         num_tx_ant_total, num_re, add_noise, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+// ---- PUSCH (nr/pusch_precoder.py, nr/pusch_channel_estimation.py) ---------------------------------------------------
+namespace {
+// y[b, t, p, re] = sum_l W[t, p, l] x[b, t, l, re]: codebook precoding of the layer grids onto the antenna ports
+__global__ void pusch_precode_kernel(const float2* __restrict__ x, const float2* __restrict__ w, float2* __restrict__ y,
+                                     long long total, int num_tx, int L, int P, long long re) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long long r = i % re;
+    long long bp = i / re;
+    int p = (int)(bp % P);
+    long long bt = bp / P;
+    int t = (int)(bt % num_tx);
+    const float2* wp = w + ((size_t)t * P + p) * L;
+    const float2* xp = x + (size_t)bt * L * re + r;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int l = 0; l < L; ++l) {
+        float2 a = wp[l], b = __ldg(xp + (size_t)l * re);
+        acc.x += a.x * b.x - a.y * b.y;
+        acc.y += a.x * b.y + a.y * b.x;
+    }
+    y[i] = acc;
+}
+
+// CDM de-spreading of LS estimates at the DMRS REs, in place. Row = one (batch', tx stream): P = num_dmrs_syms * pps
+// pilots ordered symbol-major. One thread owns one frequency group of n = 2 * num_cdm_groups_without_data consecutive
+// pilots on one DMRS symbol (single-symbol DMRS) or on a pair of adjacent DMRS symbols (double-symbol DMRS):
+//   time:  v_k = (h[s0][k] + h[s1][k]) / 2                    (dmrs_length == 2, pusch_channel_estimation.py:138-149)
+//   freq:  avg = (sum_k v_k) / 2;  h[k] = |v_k| > 0 ? avg : 0 (:153-165)
+__global__ void pusch_ls_combine_kernel(float2* __restrict__ h, long long rows, int P, int pps, int dmrs_length, int n) {
+    const int groups = pps / n;
+    const int units = (P / pps) / dmrs_length;              // symbol pairs (or single symbols) per row
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * units * groups) return;
+    int g = (int)(i % groups);
+    long long ru = i / groups;
+    int u = (int)(ru % units);
+    long long row = ru / units;
+    float2* p0 = h + (size_t)row * P + (size_t)u * dmrs_length * pps + (size_t)g * n;
+    float2* p1 = p0 + pps;
+    float2 sum = make_float2(0.f, 0.f);
+    for (int k = 0; k < n; ++k) {
+        float2 v = p0[k];
+        if (dmrs_length == 2) {
+            float2 b = p1[k];
+            v = make_float2((v.x + b.x) * 0.5f, (v.y + b.y) * 0.5f);
+            p0[k] = v;
+        }
+        sum.x += v.x;
+        sum.y += v.y;
+    }
+    float2 avg = make_float2(sum.x * 0.5f, sum.y * 0.5f);
+    for (int k = 0; k < n; ++k) {
+        float2 v = p0[k];
+        float2 o = (v.x != 0.f || v.y != 0.f) ? avg : make_float2(0.f, 0.f);
+        p0[k] = o;
+        if (dmrs_length == 2) p1[k] = o;
+    }
+}
+
+__global__ void scale_real_kernel(float* __restrict__ x, long long n, float s) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= s;
+}
+}  // namespace
+
+extern "C" int sb_pusch_precode(const float* d_x, const float* d_w, float* d_y, int64_t batch, int32_t num_tx,
+                                int32_t num_layers, int32_t num_ports, int64_t num_re, void* stream) {
+    SB_CHECK_ARG(d_x && d_w && d_y && batch >= 0 && num_tx > 0 && num_layers > 0 && num_ports > 0 && num_re > 0,
+                 "sb_pusch_precode: bad arguments");
+    long long total = batch * num_tx * (long long)num_ports * num_re;
+    if (total == 0) return SB_OK;
+    pusch_precode_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)d_x, (const float2*)d_w, (float2*)d_y, total, num_tx, num_layers, num_ports, num_re);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_pusch_ls_combine(float* d_h, float* d_err_var, int64_t rows, int32_t num_pilots,
+                                   int32_t pilots_per_dmrs_symbol, int32_t dmrs_length, int32_t group_size, void* stream) {
+    SB_CHECK_ARG(d_h && d_err_var && rows >= 0 && num_pilots > 0 && pilots_per_dmrs_symbol > 0 &&
+                     num_pilots % pilots_per_dmrs_symbol == 0 && (dmrs_length == 1 || dmrs_length == 2) &&
+                     (num_pilots / pilots_per_dmrs_symbol) % dmrs_length == 0 && group_size > 0 &&
+                     pilots_per_dmrs_symbol % group_size == 0, "sb_pusch_ls_combine: bad arguments");
+    if (rows == 0) return SB_OK;
+    long long units = (long long)rows * (num_pilots / pilots_per_dmrs_symbol / dmrs_length) *
+                      (pilots_per_dmrs_symbol / group_size);
+    pusch_ls_combine_kernel<<<grid_for(units, 256), 256, 0, (cudaStream_t)stream>>>(
+        (float2*)d_h, rows, num_pilots, pilots_per_dmrs_symbol, dmrs_length, group_size);
+    SB_LAUNCH_CHECK();
+    long long n = (long long)rows * num_pilots;
+    scale_real_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_err_var, n, dmrs_length == 2 ? 0.25f : 0.5f);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -93,6 +93,8 @@ class Block(Object):
         if hasattr(v, "shape"):
             return tuple(v.shape)
         if isinstance(v, (list, tuple)):
+            if any(hasattr(e, "shape") and not isinstance(e, np.ndarray) for e in v):
+                return [Block._get_shape(e) for e in v]       # list of tensors: list of shapes
             try:
                 return tuple(np.shape(v))
             except ValueError:
