@@ -535,6 +535,7 @@ extern "C" int sb_ldpc_decode(const sb_ldpc_graph* gc, const float* d_llr, int64
                               int32_t cn_rule, int32_t vn_rule, float offset, float llr_max, int32_t hard_out,
                               const float* d_state_in, float* d_state_out, float* d_out, void* d_ws,
                               size_t ws_bytes, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(gc && d_llr && d_out, "sb_ldpc_decode: null graph/input/output");
     SB_CHECK_ARG(batch >= 0 && num_iter >= 0, "sb_ldpc_decode: negative batch or num_iter");
     SB_CHECK_ARG(cn_rule >= SB_CN_BOXPLUS_PHI && cn_rule <= SB_CN_IDENTITY, "sb_ldpc_decode: unknown cn_rule %d", cn_rule);

@@ -735,6 +735,7 @@ __global__ void debug_phi_kernel(const float* x, float* o1, float* o2, long long
 }
 }  // namespace
 extern "C" int sb_debug_phi(const float* d_x, float* d_scalar, float* d_packed, int64_t n, void* stream) {
+    if (n == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_scalar && d_packed && n >= 0 && n % 2 == 0, "sb_debug_phi: bad arguments");
     if (n == 0) return SB_OK;
     debug_phi_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_scalar, d_packed, n);

@@ -144,6 +144,7 @@ extern "C" void sb_ldpc5g_encoder_destroy(sb_ldpc5g_encoder* e) {
 }
 
 extern "C" int sb_ldpc5g_encode(const sb_ldpc5g_encoder* ec, const float* d_u, int64_t batch, float* d_c, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(ec && d_u && d_c && batch >= 0, "sb_ldpc5g_encode: bad arguments");
     if (batch == 0) return SB_OK;
     auto* e = const_cast<sb_ldpc5g_encoder*>(ec);

@@ -470,6 +470,7 @@ int make_plan(int n, FftPlan* plan) {
 
 extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
                                 const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, int32_t shift, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_out && d_cp && d_out_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_modulate: bad arguments");
     if (rows == 0) return SB_OK;
@@ -489,6 +490,7 @@ extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, in
 extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
                                   const int32_t* d_cp, const int32_t* d_in_off, int32_t in_len, int32_t l_min,
                                   int32_t shift, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_out && d_cp && d_in_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_demodulate: bad arguments");
     if (rows == 0) return SB_OK;
@@ -507,6 +509,7 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
 
 extern "C" int sb_gather_rows(const float* d_in, const int32_t* d_idx, float* d_out, int64_t batch, int32_t rows,
                               int32_t cols_out, int32_t in_rows, int32_t cols_in, int32_t words, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_in && d_idx && d_out && batch >= 0 && rows > 0 && cols_out > 0 && cols_in > 0 &&
                      (in_rows == 1 || in_rows == rows) && (words == 1 || words == 2),
                  "sb_gather_rows: bad arguments");
@@ -523,6 +526,7 @@ extern "C" int sb_gather_rows(const float* d_in, const int32_t* d_idx, float* d_
 
 extern "C" int sb_rg_map(const float* d_x, const float* d_pilots, const int32_t* d_map, float* d_out, int64_t batch,
                          int32_t num_streams, int32_t grid_size, int32_t num_data, int32_t num_pilots, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_map && d_out && batch >= 0 && num_streams > 0 && grid_size > 0, "sb_rg_map: bad arguments");
     long long total = batch * num_streams * (long long)grid_size;
     if (total == 0) return SB_OK;
@@ -536,6 +540,7 @@ extern "C" int sb_rg_map(const float* d_x, const float* d_pilots, const int32_t*
 extern "C" int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, const float* d_pilots, const float* d_no,
                                int64_t no_inner, float* d_h, float* d_err, int64_t batch, int32_t num_streams,
                                int32_t num_pilots, int32_t grid_size, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_y && d_pilot_ind && d_pilots && d_no && d_h && d_err && batch >= 0 && num_streams > 0 &&
                      num_pilots > 0 && grid_size > 0 && no_inner >= 1, "sb_ls_at_pilots: bad arguments");
     long long total = batch * num_streams * (long long)num_pilots;
@@ -551,6 +556,7 @@ extern "C" int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32
                              const int32_t* d_fy1, const int32_t* d_ty0, const int32_t* d_ty1, const int32_t* d_npil,
                              int32_t time_avg, float* d_out, int64_t batch, int32_t num_streams, int32_t num_symbols,
                              int32_t num_subcarriers, int32_t num_pilots, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_h && d_fx0 && d_fx1 && d_fy0 && d_fy1 && d_ty0 && d_ty1 && d_npil && d_out && batch >= 0,
                  "sb_interp_lin: bad arguments");
     long long total = batch * num_streams * (long long)num_symbols * num_subcarriers;
@@ -565,6 +571,7 @@ extern "C" int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32
 extern "C" int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
                                      int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_re,
                                      int32_t add_noise, uint64_t seed, uint64_t offset, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_h && d_y && batch >= 0 && num_rx_ant_total > 0 && num_tx_ant_total > 0 && num_re > 0 &&
                      (!add_noise || (d_no && no_inner >= 1)), "sb_apply_ofdm_channel: bad arguments");
     long long total = batch * num_rx_ant_total * (long long)num_re;
@@ -643,6 +650,7 @@ __global__ void scale_real_kernel(float* __restrict__ x, long long n, float s) {
 
 extern "C" int sb_pusch_precode(const float* d_x, const float* d_w, float* d_y, int64_t batch, int32_t num_tx,
                                 int32_t num_layers, int32_t num_ports, int64_t num_re, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_w && d_y && batch >= 0 && num_tx > 0 && num_layers > 0 && num_ports > 0 && num_re > 0,
                  "sb_pusch_precode: bad arguments");
     long long total = batch * num_tx * (long long)num_ports * num_re;
@@ -655,6 +663,7 @@ extern "C" int sb_pusch_precode(const float* d_x, const float* d_w, float* d_y, 
 
 extern "C" int sb_pusch_ls_combine(float* d_h, float* d_err_var, int64_t rows, int32_t num_pilots,
                                    int32_t pilots_per_dmrs_symbol, int32_t dmrs_length, int32_t group_size, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_h && d_err_var && rows >= 0 && num_pilots > 0 && pilots_per_dmrs_symbol > 0 &&
                      num_pilots % pilots_per_dmrs_symbol == 0 && (dmrs_length == 1 || dmrs_length == 2) &&
                      (num_pilots / pilots_per_dmrs_symbol) % dmrs_length == 0 && group_size > 0 &&
@@ -682,6 +691,7 @@ static int lmmse_threads(int M, int K, size_t* smem) {
 
 extern "C" int sb_lmmse_equalize(const float* d_y, const float* d_h, const float* d_s, float* d_x_hat, float* d_no_eff,
                                  int64_t num, int32_t M, int32_t K, void* stream) {
+    if (num == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_y && d_h && d_s && d_x_hat && d_no_eff && num >= 0 && M >= 1 && K >= 1 && K <= 16 && K <= M,
                  "sb_lmmse_equalize: bad arguments (need 1 <= K <= 16, K <= M)");
     if (num == 0) return SB_OK;
@@ -702,6 +712,7 @@ extern "C" int sb_ofdm_lmmse(const float* d_y, const float* d_h_hat, const float
                              float* d_x_hat, float* d_no_eff, int64_t batch, int32_t num_rx, int32_t num_rx_ant,
                              int32_t num_tx_streams, int32_t num_symbols, int32_t num_subcarriers,
                              int32_t streams_per_rx, int32_t interferers_per_rx, int32_t num_data, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_y && d_h_hat && d_err_var && h_ev_stride && d_no && h_no_stride && d_desired && d_out_stream &&
                      d_data_pos && d_x_hat && d_no_eff && batch >= 0 && streams_per_rx >= 1 && streams_per_rx <= 16 &&
                      streams_per_rx <= num_rx_ant && (interferers_per_rx == 0 || d_undesired),

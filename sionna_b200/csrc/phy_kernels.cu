@@ -243,6 +243,7 @@ inline int grid_for(long long work_items, int threads) {
 }  // namespace
 
 extern "C" int sb_binary_source(float* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (n == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_out && n >= 0, "sb_binary_source: bad arguments");
     if (n == 0) return SB_OK;
     binary_source_kernel<<<grid_for((n + 127) / 128, 128), 128, 0, (cudaStream_t)stream>>>(d_out, n, seed, offset);
@@ -252,6 +253,7 @@ extern "C" int sb_binary_source(float* d_out, int64_t n, uint64_t seed, uint64_t
 
 extern "C" int sb_qam_map(const float* d_bits, const float* d_points, int32_t m, float* d_out, int32_t* d_idx_out,
                           int64_t n_sym, void* stream) {
+    if (n_sym == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_bits && d_points && d_out && m >= 1 && m <= 12 && n_sym >= 0, "sb_qam_map: bad arguments");
     if (n_sym == 0) return SB_OK;
     size_t smem = sizeof(float2) << m;
@@ -264,6 +266,7 @@ extern "C" int sb_qam_map(const float* d_bits, const float* d_points, int32_t m,
 extern "C" int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, const float* d_points, int32_t m,
                         int32_t method, const float* d_prior, int64_t prior_inner, float* d_llr, int64_t n_sym,
                         int32_t hard_out, void* stream) {
+    if (n_sym == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_y && d_no && d_points && d_llr && m >= 1 && m <= 12 && n_sym >= 0 && no_inner >= 1,
                  "sb_demap: bad arguments");
     SB_CHECK_ARG(method == 0 || method == 1, "sb_demap: method must be 0 (app) or 1 (maxlog)");
@@ -283,6 +286,7 @@ extern "C" int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, c
 
 extern "C" int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, int64_t n, uint64_t seed,
                        uint64_t offset, void* stream) {
+    if (n == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_no && d_y && n >= 0 && no_inner >= 1, "sb_awgn: bad arguments");
     if (n == 0) return SB_OK;
     awgn_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)d_x, d_no, no_inner,
@@ -292,6 +296,7 @@ extern "C" int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, fl
 }
 
 extern "C" int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint64_t seed, uint64_t offset, void* stream) {
+    if (n == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_out && n >= 0, "sb_normal: bad arguments");
     if (n == 0) return SB_OK;
     normal_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(d_out, n, mean, stddev, seed, offset);
@@ -301,6 +306,7 @@ extern "C" int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint
 
 extern "C" int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_t k, int64_t* d_counters,
                                void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_b && d_b_hat && d_counters && rows >= 0 && k >= 1, "sb_count_errors: bad arguments");
     if (rows == 0) return SB_OK;
     count_errors_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -311,6 +317,7 @@ extern "C" int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t r
 
 extern "C" int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, int32_t k, int32_t crc_length, float* d_out,
                              int64_t rows, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_bits && d_gen_rows && d_out && k >= 1 && crc_length >= 1 && crc_length <= 32 && rows >= 0,
                  "sb_crc_encode: bad arguments");
     if (rows == 0) return SB_OK;
@@ -321,6 +328,7 @@ extern "C" int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, in
 
 extern "C" int sb_scramble(const float* d_x, const float* d_seq, int32_t binary, float* d_out, int64_t rows, int32_t n,
                            int32_t seq_rows, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_seq && d_out && rows >= 0 && n >= 1 && seq_rows >= 1, "sb_scramble: bad arguments");
     if (rows == 0) return SB_OK;
     scramble_kernel<<<grid_for(rows * n, 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_seq, binary, d_out, rows, n, seq_rows);

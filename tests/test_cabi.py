@@ -51,3 +51,13 @@ def test_blocks_fail_loudly_without_cuda():
         dec(np.zeros((2, 100), np.float32))
     with pytest.raises(RuntimeError):
         Mapper("qam", 2)(np.zeros((2, 4), np.float32))
+
+
+def test_empty_batches_are_accepted_without_a_device(sb_lib):
+    """Every batch-taking entry point returns SB_OK for an empty batch before touching pointers or the device."""
+    assert sb_lib.sb_awgn(None, None, 1, None, 0, 0, 0, None) == 0
+    assert sb_lib.sb_binary_source(None, 0, 0, 0, None) == 0
+    assert sb_lib.sb_ldpc5g_encode(None, None, 0, None, None) == 0
+    assert sb_lib.sb_ldpc_decode(None, None, 0, 20, 0, 0, 0.0, 20.0, 1, None, None, None, None, 0, None) == 0
+    assert sb_lib.sb_count_errors(None, None, 0, 8, None, None) == 0
+    assert sb_lib.sb_pusch_precode(None, None, None, 0, 1, 1, 2, 12, None) == 0
