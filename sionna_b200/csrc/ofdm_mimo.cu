@@ -588,22 +588,23 @@ namespace {
 // y[b, t, p, re] = sum_l W[t, p, l] x[b, t, l, re]: codebook precoding of the layer grids onto the antenna ports
 __global__ void pusch_precode_kernel(const float2* __restrict__ x, const float2* __restrict__ w, float2* __restrict__ y,
                                      long long total, int num_tx, int L, int P, long long re) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    long long r = i % re;
-    long long bp = i / re;
-    int p = (int)(bp % P);
-    long long bt = bp / P;
-    int t = (int)(bt % num_tx);
-    const float2* wp = w + ((size_t)t * P + p) * L;
-    const float2* xp = x + (size_t)bt * L * re + r;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int l = 0; l < L; ++l) {
-        float2 a = wp[l], b = __ldg(xp + (size_t)l * re);
-        acc.x += a.x * b.x - a.y * b.y;
-        acc.y += a.x * b.y + a.y * b.x;
+    // grid-stride: grid_for() caps the grid at 16 CTAs per SM
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i % re;
+        long long bp = i / re;
+        int p = (int)(bp % P);
+        long long bt = bp / P;
+        int t = (int)(bt % num_tx);
+        const float2* wp = w + ((size_t)t * P + p) * L;
+        const float2* xp = x + (size_t)bt * L * re + r;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            float2 a = wp[l], b = __ldg(xp + (size_t)l * re);
+            acc.x += a.x * b.x - a.y * b.y;
+            acc.y += a.x * b.y + a.y * b.x;
+        }
+        y[i] = acc;
     }
-    y[i] = acc;
 }
 
 // CDM de-spreading of LS estimates at the DMRS REs, in place. Row = one (batch', tx stream): P = num_dmrs_syms * pps
@@ -614,37 +615,38 @@ __global__ void pusch_precode_kernel(const float2* __restrict__ x, const float2*
 __global__ void pusch_ls_combine_kernel(float2* __restrict__ h, long long rows, int P, int pps, int dmrs_length, int n) {
     const int groups = pps / n;
     const int units = (P / pps) / dmrs_length;              // symbol pairs (or single symbols) per row
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * units * groups) return;
-    int g = (int)(i % groups);
-    long long ru = i / groups;
-    int u = (int)(ru % units);
-    long long row = ru / units;
-    float2* p0 = h + (size_t)row * P + (size_t)u * dmrs_length * pps + (size_t)g * n;
-    float2* p1 = p0 + pps;
-    float2 sum = make_float2(0.f, 0.f);
-    for (int k = 0; k < n; ++k) {
-        float2 v = p0[k];
-        if (dmrs_length == 2) {
-            float2 b = p1[k];
-            v = make_float2((v.x + b.x) * 0.5f, (v.y + b.y) * 0.5f);
-            p0[k] = v;
+    const long long total = rows * units * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int g = (int)(i % groups);
+        long long ru = i / groups;
+        int u = (int)(ru % units);
+        long long row = ru / units;
+        float2* p0 = h + (size_t)row * P + (size_t)u * dmrs_length * pps + (size_t)g * n;
+        float2* p1 = p0 + pps;
+        float2 sum = make_float2(0.f, 0.f);
+        for (int k = 0; k < n; ++k) {
+            float2 v = p0[k];
+            if (dmrs_length == 2) {
+                float2 b = p1[k];
+                v = make_float2((v.x + b.x) * 0.5f, (v.y + b.y) * 0.5f);
+                p0[k] = v;
+            }
+            sum.x += v.x;
+            sum.y += v.y;
         }
-        sum.x += v.x;
-        sum.y += v.y;
-    }
-    float2 avg = make_float2(sum.x * 0.5f, sum.y * 0.5f);
-    for (int k = 0; k < n; ++k) {
-        float2 v = p0[k];
-        float2 o = (v.x != 0.f || v.y != 0.f) ? avg : make_float2(0.f, 0.f);
-        p0[k] = o;
-        if (dmrs_length == 2) p1[k] = o;
+        float2 avg = make_float2(sum.x * 0.5f, sum.y * 0.5f);
+        for (int k = 0; k < n; ++k) {
+            float2 v = p0[k];
+            float2 o = (v.x != 0.f || v.y != 0.f) ? avg : make_float2(0.f, 0.f);
+            p0[k] = o;
+            if (dmrs_length == 2) p1[k] = o;
+        }
     }
 }
 
 __global__ void scale_real_kernel(float* __restrict__ x, long long n, float s) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= s;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] *= s;
 }
 }  // namespace
 

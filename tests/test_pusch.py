@@ -244,7 +244,8 @@ def test_pusch_ls_channel_estimator_vs_oracle(cuda_device, config_type, length, 
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scenario", ["siso_awgn", "mimo_2x2layers_8ant", "codebook_perfect_csi", "time_domain"])
+@pytest.mark.parametrize("scenario", ["siso_awgn", "mimo_2x2layers_8ant", "codebook_perfect_csi", "time_domain",
+                                      "tdl_large_batch"])
 def test_pusch_link_end_to_end(cuda_device, scenario):
     """BASELINE.json configs[4]: PUSCHTransmitter -> channel -> PUSCHReceiver recovers every transport block at high SNR
     (reference: test_pusch_receiver.py)."""
@@ -276,6 +277,21 @@ def test_pusch_link_end_to_end(cuda_device, scenario):
         rx = PUSCHReceiver(tx, input_domain="time", l_min=0, return_tb_crc_status=True)
         x, b = tx(batch)                                                     # [batch, 1, 1, time samples]
         y = AWGN()(x, 0.002)
+        b_hat, crc = rx(y, 0.002)
+    elif scenario == "tdl_large_batch":
+        # the configuration of tools/pusch_sim.py at a batch that exceeds one wave of every element-wise kernel
+        from sionna_b200.phy.channel import ApplyOFDMChannel, TDL, subcarrier_frequencies, cir_to_ofdm_channel
+        batch = 2048
+        pc = PUSCHConfig(num_layers=2, num_antenna_ports=2)
+        pc.carrier.n_size_grid = 16
+        pc.dmrs.additional_position = 1
+        tx = PUSCHTransmitter(pc)
+        rx = PUSCHReceiver(tx, return_tb_crc_status=True)
+        rg = tx.resource_grid
+        x, b = tx(batch)
+        a, tau = TDL("B", 100e-9, 3.5e9, num_rx_ant=8, num_tx_ant=2)(batch, 14, 1.0)
+        h = cir_to_ofdm_channel(subcarrier_frequencies(rg.fft_size, rg.subcarrier_spacing), a, tau, normalize=True)
+        y = ApplyOFDMChannel()(x, h, 0.002)
         b_hat, crc = rx(y, 0.002)
     elif scenario == "mimo_2x2layers_8ant":
         pcs = []
