@@ -155,6 +155,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner / debug lines off stdout
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "--gpus must match the torchrun world size"
 

@@ -36,6 +36,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner / debug lines off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         ge.build()
