@@ -142,6 +142,12 @@ int sb_qam_map(const float* d_bits, const float* d_points, int32_t m, float* d_o
  *   d_llr [n_sym * m] logits log p(1)/p(0), or hard decisions (llr > 0) when hard_out != 0. */
 int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, const float* d_points, int32_t m, int32_t method,
              const float* d_prior, int64_t prior_inner, float* d_llr, int64_t n_sym, int32_t hard_out, void* stream);
+/* Demapper.call for separable constellations (all square QAMs of mapping.py:104-117), no prior: the label's even bits
+ * select the real level d_levels_re[t], the odd bits the imaginary level d_levels_im[t] (t = those m/2 bits, MSB
+ * first). Same LLRs as sb_demap up to fp32 rounding with 2^(m/2) instead of 2^m exponents per dimension. */
+int sb_demap_qam(const float* d_y, const float* d_no, int64_t no_inner, const float* d_levels_re,
+                 const float* d_levels_im, int32_t m, int32_t method, float* d_llr, int64_t n_sym, int32_t hard_out,
+                 void* stream);
 /* AWGN.call (channel/awgn.py:63-78, utils/misc.py:19-54): y = x + sqrt(no) * CN(0,1), complex64 [n];
  * element i uses d_no[i / no_inner]. */
 int sb_awgn(const float* d_x, const float* d_no, int64_t no_inner, float* d_y, int64_t n, uint64_t seed,

@@ -17,6 +17,9 @@ def _lib():
         h.sbo_demap.restype = None
         h.sbo_demap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                 C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int]
+        h.sbo_demap_qam.restype = None
+        h.sbo_demap_qam.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_int64, C.c_int]
         h._map_ready = True
     return h
 
@@ -57,14 +60,45 @@ def mapper(bits, points):                                          # mapping.py:
     return points[idx], idx
 
 
+def separable_levels(points):
+    """(levels_re, levels_im) if points[j] = levels_re[even label bits of j] + 1j * levels_im[odd label bits of j]
+    exactly (every square QAM of mapping.py:104-117), else None. Bits are counted MSB first."""
+    pts = np.asarray(points)
+    m = int(np.log2(len(pts)))
+    if m < 2 or m % 2 or m > 10:
+        return None
+    h = m // 2
+    j = np.arange(len(pts))
+    bits = (j[:, None] >> np.arange(m - 1, -1, -1)) & 1                # [2^m, m] MSB first
+    w = 1 << np.arange(h - 1, -1, -1)
+    jr, ji = bits[:, 0::2] @ w, bits[:, 1::2] @ w
+    lev_re = np.zeros(1 << h, np.float32)
+    lev_im = np.zeros(1 << h, np.float32)
+    lev_re[jr[ji == 0]] = pts.real[ji == 0]
+    lev_im[ji[jr == 0]] = pts.imag[jr == 0]
+    if np.array_equal(lev_re[jr].astype(np.float32), pts.real.astype(np.float32)) and \
+            np.array_equal(lev_im[ji].astype(np.float32), pts.imag.astype(np.float32)):
+        return lev_re, lev_im
+    return None
+
+
 def demapper(y, no, points, method="app", prior=None, hard_out=False, math_mode=0):
-    """y [..., S] complex64, no scalar or broadcastable to y, prior None | [m] | [..., S, m] -> llr [..., S*m]."""
+    """y [..., S] complex64, no scalar or broadcastable to y, prior None | [m] | [..., S, m] -> llr [..., S*m].
+    math_mode 0: the reference's 2-D formula with libm; math_mode 1: what the CUDA kernels evaluate (the separable form
+    for square QAM without prior, the 2-D formula with sb_math.h otherwise)."""
     y = np.ascontiguousarray(y, np.complex64)
     m = int(np.log2(len(points)))
     pts = np.ascontiguousarray(points, np.complex64)
     n_sym = y.size
     no_b = np.ascontiguousarray(np.broadcast_to(np.asarray(no, np.float32).reshape(
         np.shape(no) + (1,) * (y.ndim - np.ndim(no))), y.shape), np.float32)
+    sep = separable_levels(pts) if (math_mode == 1 and prior is None) else None
+    if sep is not None:
+        llr = np.empty(y.shape[:-1] + (y.shape[-1] * m,), np.float32)
+        lr, li = np.ascontiguousarray(sep[0]), np.ascontiguousarray(sep[1])
+        _lib().sbo_demap_qam(y.ctypes.data, no_b.ctypes.data, 1, lr.ctypes.data, li.ctypes.data, m,
+                             0 if method == "app" else 1, llr.ctypes.data, n_sym, int(hard_out))
+        return llr
     pr = None
     inner = 1
     if prior is not None:

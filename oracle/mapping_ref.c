@@ -78,3 +78,47 @@ void sbo_demap(const float* y, const float* no, int64_t no_inner, const float* p
         }
     }
 }
+
+
+/* Kernel-math restatement of the separable-QAM demapper (csrc/phy_kernels.cu demap_qam_kernel): mathematically the same
+ * LLRs as sbo_demap (exp(e_j) factors into a real and an imaginary part and the other dimension's factor cancels), with
+ * the operation order the CUDA kernel uses, so the two agree bit for bit. lev_re / lev_im: 2^(m/2) PAM levels indexed
+ * by the even / odd label bits (MSB first). Always evaluated with sb_math.h (this path has no reference-order twin; the
+ * reference-order value is sbo_demap with math_mode 0). */
+void sbo_demap_qam(const float* y, const float* no, int64_t no_inner, const float* lev_re, const float* lev_im, int m,
+                   int method, float* llr, int64_t n_sym, int hard_out) {
+    const int H = m / 2, L = 1 << H;
+    const float tiny = 1.17549435e-38f;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < n_sym; ++s) {
+        float inv_n0 = 1.0f / fmaxf(no[s / no_inner], tiny);
+        for (int d = 0; d < 2; ++d) {
+            float yd = y[2 * s + d];
+            float e[32];
+            for (int t = 0; t < L; ++t) {
+                float dd = yd - (d ? lev_im[t] : lev_re[t]);
+                e[t] = -(dd * dd) * inv_n0;
+            }
+            for (int u = 0; u < H; ++u) {
+                int mask = 1 << (H - 1 - u);
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+                for (int t = 0; t < L; ++t) { if (t & mask) mx1 = fmaxf(mx1, e[t]); else mx0 = fmaxf(mx0, e[t]); }
+                float l;
+                if (method == 1) {
+                    l = mx1 - mx0;
+                } else {
+                    mx0 = isfinite(mx0) ? mx0 : 0.f;
+                    mx1 = isfinite(mx1) ? mx1 : 0.f;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int t = 0; t < L; ++t) {                  /* ascending t within each group */
+                        if (t & mask) s1 += sb_expf(e[t] - mx1); else s0 += sb_expf(e[t] - mx0);
+                    }
+                    float b1 = (s1 > 0.f ? sb_logf(s1) : -INFINITY) + mx1;
+                    float b0 = (s0 > 0.f ? sb_logf(s0) : -INFINITY) + mx0;
+                    l = b1 - b0;
+                }
+                llr[s * m + 2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
+            }
+        }
+    }
+}

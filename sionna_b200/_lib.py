@@ -36,6 +36,7 @@ SIGNATURES = {
     "sb_normal": (i32, [vp, i64, f32, f32, u64, u64, vp]),
     "sb_qam_map": (i32, [vp, vp, i32, vp, vp, i64, vp]),
     "sb_demap": (i32, [vp, vp, i64, vp, i32, i32, vp, i64, vp, i64, i32, vp]),
+    "sb_demap_qam": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, i64, i32, vp]),
     "sb_awgn": (i32, [vp, vp, i64, vp, i64, u64, u64, vp]),
     "sb_count_errors": (i32, [vp, vp, i64, i32, vp, vp]),
     "sb_crc_encode": (i32, [vp, vp, i32, i32, vp, i64, vp]),

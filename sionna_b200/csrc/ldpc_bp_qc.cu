@@ -437,8 +437,12 @@ __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint
     if (with_fused) vn_class<MODE, 10, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
 }
 
+// Threads per CTA. 24 warps (80 registers/thread) for every rule: 30 warps at 64 registers were measured for the min-sum
+// kernels and lost 7 % (5.32 vs 4.97 ms / 4096 codewords: more barrier and spill time than latency hiding gained).
+__host__ __device__ constexpr int qc_max_threads(int rule) { return rule >= SB_CN_MINSUM ? 768 : 768; }
+
 template <int RULE, int REP>                              // REP: copies of the phi log table (32 or 1)
-__global__ void __launch_bounds__(768, 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
+__global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int Z = p.Z, N = p.N, Zb = (Z + 31) >> 5;
@@ -576,7 +580,10 @@ int qc_ensure_uploaded(sb_ldpc_graph* g) {
 
 template <int RULE>
 int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = (RULE == SB_CN_BOXPLUS_PHI && p.tab_rep == 1) ? ldpc_bp_qc_kernel<RULE, 1> : ldpc_bp_qc_kernel<RULE, 32>;
+    auto kern = ldpc_bp_qc_kernel<RULE, 32>;
+    if constexpr (RULE == SB_CN_BOXPLUS_PHI) {
+        if (p.tab_rep == 1) kern = ldpc_bp_qc_kernel<RULE, 1>;
+    }
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -772,7 +779,8 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     p.offset = offset; p.llr_max = llr_max; p.tab_rep = tab_rep;
     p.use_tma = (g->n_in % 4 == 0) && (g->n_in <= p.E_alloc) && ((reinterpret_cast<uintptr_t>(d_llr) & 15) == 0);
     const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
-    int groups = std::max(1, std::min(24 / Zb, std::max(g->qc_rows, g->qc_cols)));
+    const int max_warps = qc_max_threads(cn_rule) / 32;
+    int groups = std::max(1, std::min(max_warps / Zb, std::max(g->qc_rows, g->qc_cols)));
     const int threads = groups * Zb * 32;                  // every warp owns one slice index for the whole launch
     for (int k = 0; k < kRowClasses; ++k) p.row_cls_mod[k] = (k ? g->qc_row_cls_end[k - 1] : 0) % groups;
     for (int k = 0; k < kColClasses; ++k) p.col_cls_mod[k] = (k ? g->qc_col_cls_end[k - 1] : 0) % groups;

@@ -21,6 +21,9 @@
 #include <algorithm>
 #include <vector>
 #include "sb_common.h"
+#include <map>
+#include <mutex>
+#include <vector>
 #include "rng.cuh"
 
 namespace {
@@ -156,6 +159,109 @@ __global__ void ofdm_demod_kernel(const float2* __restrict__ x, float2* __restri
             float2 v = cmul(cscale(res[k], scale), PC[k]);
             dst[ks] = v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FFT sizes up to 1024 (every OFDM grid up to 85 PRB, e.g. 72, 76, 128, 180, 600): one WARP per transform, several
+// transforms per CTA, no CTA-wide barrier in the loop. A stage of radix p computes each of the N outputs as a p-term
+// DFT sum (lanes stride over the outputs); all index arithmetic of the Stockham permutation comes from per-stage tables
+// built on the host (input base, twiddle index, root step: 3 x uint16 per output), so the inner loop is
+// 2 shared loads + 1 complex multiply-add.
+// ---------------------------------------------------------------------------------------------------------------
+struct SmallFftPlan {
+    int n, n_stages;
+    int p[12], rstride[12];
+    const unsigned short* tab;       // [n_stages][3][n]: in_base, twiddle index, root step
+};
+
+__device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const float2* __restrict__ W,
+                                                  const unsigned short* __restrict__ tab, const SmallFftPlan& plan, int lane) {
+    const int N = plan.n;
+    for (int st = 0; st < plan.n_stages; ++st) {
+        const int p = plan.p[st], rs = plan.rstride[st];
+        const unsigned short* t_in = tab + (size_t)st * 3 * N;
+        const unsigned short* t_tw = t_in + N;
+        const unsigned short* t_cs = t_tw + N;
+        for (int o = lane; o < N; o += 32) {
+            const int in = t_in[o], cs = t_cs[o];
+            float2 acc = x[in];                                    // r = 0: root index 0 -> W = 1
+            int widx = cs;
+            for (int r = 1; r < p; ++r) {
+                acc = cadd(acc, cmul(x[in + r * rs], W[widx]));
+                widx += cs;
+                if (widx >= N) widx -= N;
+            }
+            y[o] = cmul(acc, W[t_tw[o]]);
+        }
+        __syncwarp();
+        float2* t = x; x = y; y = t;
+    }
+    return x;
+}
+
+template <int DEMOD>
+__global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __restrict__ x, float2* __restrict__ out,
+                                                             SmallFftPlan plan, int nsym, const int* __restrict__ cp,
+                                                             const int* __restrict__ off, int len, int l_min,
+                                                             long long rows, int shift) {
+    extern __shared__ float2 sm[];
+    const int N = plan.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    float2* W = sm;
+    float2* PC = sm + N;                                           // phase compensation (demodulator only)
+    float2* bufs = sm + (DEMOD ? 2 : 1) * N;
+    unsigned short* tab = reinterpret_cast<unsigned short*>(bufs + (size_t)2 * N * nwarps);
+    for (int k = tid; k < N; k += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
+        W[k] = make_float2(cs, sn);
+        if (DEMOD) {
+            float tmp = -2.0f * 3.14159265358979323846f * (float)l_min / (float)N * (float)k;
+            PC[k] = make_float2(cosf(tmp), sinf(tmp));
+        }
+    }
+    for (int i = tid; i < plan.n_stages * 3 * N; i += blockDim.x) tab[i] = plan.tab[i];
+    __syncthreads();
+    float2* b0 = bufs + (size_t)2 * N * warp;
+    float2* b1 = b0 + N;
+    const float scale = 1.0f / sqrtf((float)N);
+    const long long jobs = rows * nsym;
+    for (long long job = (long long)blockIdx.x * nwarps + warp; job < jobs; job += (long long)gridDim.x * nwarps) {
+        const int l = (int)(job % nsym);
+        if (DEMOD) {
+            const float2* src = x + (job / nsym) * len + off[l] + cp[l];
+            for (int k = lane; k < N; k += 32) b0[k] = src[k];
+        } else {
+            const float2* src = x + job * N;
+            const int h = N / 2;
+            for (int k = lane; k < N; k += 32) {
+                int ks = k;
+                if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // ifftshift
+                float2 v = src[ks];
+                b0[k] = make_float2(v.x, -v.y);                    // ifft = conj(fft(conj(x))) / N
+            }
+        }
+        __syncwarp();
+        const float2* res = fft_small_warp(b0, b1, W, tab, plan, lane);
+        if (DEMOD) {
+            float2* dst = out + job * N;
+            const int h = N / 2;
+            for (int k = lane; k < N; k += 32) {
+                int ks = k;
+                if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // fftshift
+                dst[ks] = cmul(cscale(res[k], scale), PC[k]);
+            }
+        } else {
+            const int c = cp[l];
+            float2* dst = out + (job / nsym) * len + off[l];
+            for (int i = lane; i < N + c; i += 32) {
+                int k = i - c;
+                if (k < 0) k += N;
+                float2 v = res[k];
+                dst[i] = make_float2(v.x * scale, -v.y * scale);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -453,6 +559,126 @@ __global__ void ofdm_lmmse_kernel(const OfdmEqParams p) {
     }
 }
 
+// Fast path of ofdm_lmmse_kernel for receivers without interfering streams (KU == 0): S = diag(no + sum err_var) is
+// diagonal, whitening is a per-antenna scaling, and everything fits in registers. One thread per resource element
+// streams once over the antennas (reads coalesced over the subcarrier index) and accumulates
+//   B = H_w^H H_w (K x K Hermitian, lower triangle) and z = H_w^H y_w,          H_w = H / sqrt(d), y_w = y / sqrt(d)
+// then A = B + I = C C^H, A^-1 = C^-H C^-1 and, without forming G = A^-1 H_w^H (K x M),
+//   G y_w = A^-1 z,   diag(G H_w)_k = sum_j (A^-1)_kj B_jk          (same quantities as lmmse_core)
+template <int K>
+__global__ void __launch_bounds__(128) ofdm_lmmse_diag_kernel(const OfdmEqParams p) {
+    const long long SF = (long long)p.S * p.F;
+    const long long total = p.B * p.RX * SF;
+    const int M = p.ANT;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long re = i % SF;
+        int rx = (int)((i / SF) % p.RX);
+        long long b = i / (SF * p.RX);
+        int s = (int)(re / p.F), f = (int)(re % p.F);
+        int ts[K], dp[K];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ts[k] = p.out_ts[rx * K + k];
+            dp[k] = p.data_pos[(size_t)ts[k] * SF + re];
+            any = any || dp[k] >= 0;
+        }
+        if (!any) continue;
+        int des[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) des[k] = p.des[rx * K + k];
+        float2 Bm[K * (K + 1) / 2];                             // lower triangle, row a: entries (a, 0..a)
+        float2 z[K];
+#pragma unroll
+        for (int e = 0; e < K * (K + 1) / 2; ++e) Bm[e] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = make_float2(0.f, 0.f);
+        for (int m = 0; m < M; ++m) {
+            const long long row = (b * p.RX + rx) * M + m;
+            float evs = 0.f;
+            for (int q = 0; q < p.TXS; ++q)
+                evs += p.ev[b * p.ev_stride[0] + rx * p.ev_stride[1] + m * p.ev_stride[2] + q * p.ev_stride[3] +
+                            s * p.ev_stride[4] + f * p.ev_stride[5]];
+            // whitening by 1 / sqrt(d): one division per antenna, multiplications for the K + 1 scalings
+            const float w = 1.0f / sqrtf(p.no[b * p.no_stride[0] + rx * p.no_stride[1] + m * p.no_stride[2]] + evs);
+            float2 yw = p.y[row * SF + re];
+            yw = make_float2(yw.x * w, yw.y * w);
+            float2 hw[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float2 v = p.hhat[(row * p.TXS + des[k]) * SF + re];
+                hw[k] = make_float2(v.x * w, v.y * w);
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                z[a] = cadd(z[a], cmulc(yw, hw[a]));               // conj(H_w[m, a]) * y_w[m]
+#pragma unroll
+                for (int c = 0; c <= a; ++c) Bm[a * (a + 1) / 2 + c] = cadd(Bm[a * (a + 1) / 2 + c], cmulc(hw[c], hw[a]));
+            }
+        }
+        // A = B + I = C C^H (lower, in registers)
+        float2 C[K * (K + 1) / 2];
+#pragma unroll
+        for (int e = 0; e < K * (K + 1) / 2; ++e) C[e] = Bm[e];
+#pragma unroll
+        for (int a = 0; a < K; ++a) C[a * (a + 1) / 2 + a].x += 1.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            float dj = C[j * (j + 1) / 2 + j].x;
+#pragma unroll
+            for (int k = 0; k < j; ++k) { float2 l = C[j * (j + 1) / 2 + k]; dj -= l.x * l.x + l.y * l.y; }
+            dj = sqrtf(dj);
+            C[j * (j + 1) / 2 + j] = make_float2(dj, 0.f);
+#pragma unroll
+            for (int r = j + 1; r < K; ++r) {
+                float2 v = C[r * (r + 1) / 2 + j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v = csub(v, cmulc(C[r * (r + 1) / 2 + k], C[j * (j + 1) / 2 + k]));
+                C[r * (r + 1) / 2 + j] = make_float2(v.x / dj, v.y / dj);
+            }
+        }
+        // Ci = C^-1 (lower), column by column
+        float2 Ci[K * (K + 1) / 2];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+#pragma unroll
+            for (int r = c; r < K; ++r) {
+                float2 v = make_float2(r == c ? 1.f : 0.f, 0.f);
+#pragma unroll
+                for (int k = c; k < r; ++k) v = csub(v, cmul(C[r * (r + 1) / 2 + k], Ci[k * (k + 1) / 2 + c]));
+                float dr = C[r * (r + 1) / 2 + r].x;
+                Ci[r * (r + 1) / 2 + c] = make_float2(v.x / dr, v.y / dr);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            // row k of A^-1 = C^-H C^-1: (A^-1)_kj = sum_{r >= max(k, j)} conj(Ci[r, k]) Ci[r, j]
+            float2 gy = make_float2(0.f, 0.f), dd = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                float2 ainv = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = (k > j ? k : j); r < K; ++r)
+                    ainv = cadd(ainv, cmulc(Ci[r * (r + 1) / 2 + j], Ci[r * (r + 1) / 2 + k]));
+                gy = cadd(gy, cmul(ainv, z[j]));
+                // B_jk: stored lower triangle, B_jk = conj(B_kj)
+                float2 bjk = j >= k ? Bm[j * (j + 1) / 2 + k] : make_float2(Bm[k * (k + 1) / 2 + j].x, -Bm[k * (k + 1) / 2 + j].y);
+                dd = cadd(dd, cmul(ainv, bjk));
+            }
+            if (dp[k] >= 0) {
+                float2 inv = cdiv(make_float2(1.f, 0.f), dd);
+                p.xh[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = cdiv(gy, dd);
+                p.ne[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = inv.x - 1.f;
+            }
+        }
+    }
+}
+
+template <int K>
+void launch_lmmse_diag(const OfdmEqParams& p, long long total, cudaStream_t stream) {
+    ofdm_lmmse_diag_kernel<K><<<grid_for(total, 128), 128, 0, stream>>>(p);
+}
+
 int make_plan(int n, FftPlan* plan) {
     plan->n = n;
     plan->n_radix = 0;
@@ -468,12 +694,80 @@ int make_plan(int n, FftPlan* plan) {
 
 }  // namespace
 
+namespace {
+// Host side of the small-FFT path: stage tables per size, built once and kept on the device.
+struct SmallPlanEntry { SmallFftPlan plan; };
+std::mutex g_small_plan_mutex;
+std::map<int, SmallPlanEntry> g_small_plans;
+
+int get_small_plan(int n, SmallFftPlan* out) {
+    std::lock_guard<std::mutex> lock(g_small_plan_mutex);
+    auto it = g_small_plans.find(n);
+    if (it != g_small_plans.end()) { *out = it->second.plan; return SB_OK; }
+    FftPlan fp;
+    if (make_plan(n, &fp) != 0 || fp.n_radix > 12) { sb_set_error("fft size %d has too many factors", n); return SB_EUNSUPPORTED; }
+    SmallFftPlan sp{};
+    sp.n = n;
+    sp.n_stages = fp.n_radix;
+    std::vector<unsigned short> tab((size_t)fp.n_radix * 3 * n);
+    int cur = n, span = 1;
+    for (int st = 0; st < fp.n_radix; ++st) {
+        const int p = fp.radix[st], m = cur / p;
+        sp.p[st] = p;
+        sp.rstride[st] = span * m;
+        for (int o = 0; o < n; ++o) {                              // output o = q + span * (p * k + c)
+            const int q = o % span, t = o / span, c = t % p, k = t / p;
+            tab[((size_t)st * 3 + 0) * n + o] = (unsigned short)(q + span * k);
+            tab[((size_t)st * 3 + 1) * n + o] = (unsigned short)(((long long)c * k * span) % n);
+            tab[((size_t)st * 3 + 2) * n + o] = (unsigned short)(((long long)c * (n / p)) % n);
+        }
+        cur = m;
+        span *= p;
+    }
+    unsigned short* d = nullptr;
+    SB_CUDA(cudaMalloc((void**)&d, tab.size() * sizeof(unsigned short)));
+    SB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    sp.tab = d;
+    g_small_plans[n] = SmallPlanEntry{sp};
+    *out = sp;
+    return SB_OK;
+}
+
+constexpr int kSmallFftMax = 1024;
+
+template <int DEMOD>
+int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* cp, const int* off, int len, int l_min,
+                     long long rows, int shift, cudaStream_t stream) {
+    SmallFftPlan sp;
+    int rc = get_small_plan(n, &sp);
+    if (rc) return rc;
+    const int warps = 8;
+    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * warps) + sizeof(unsigned short) * 3 * (size_t)n * sp.n_stages;
+    auto kern = ofdm_fft_small_kernel<DEMOD>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+    long long jobs = rows * nsym;
+    long long want = (jobs + warps - 1) / warps;
+    int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sb_num_sms() * std::max(1, occ)));
+    kern<<<grid, warps * 32, smem, stream>>>(x, out, sp, nsym, cp, off, len, l_min, rows, shift);
+    return SB_OK;
+}
+}  // namespace
+
 extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
                                 const int32_t* d_cp, const int32_t* d_out_off, int32_t out_len, int32_t shift, void* stream) {
     if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_x && d_out && d_cp && d_out_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_modulate: bad arguments");
     if (rows == 0) return SB_OK;
+    if (fft_size <= kSmallFftMax) {
+        int rc = launch_fft_small<0>((const float2*)d_x, (float2*)d_out, fft_size, num_symbols, d_cp, d_out_off, out_len, 0,
+                                     rows, shift, (cudaStream_t)stream);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        return SB_OK;
+    }
     FftPlan plan;
     SB_CHECK_ARG(make_plan(fft_size, &plan) == 0, "sb_ofdm_modulate: fft_size has too many factors");
     int threads = std::min(256, std::max(32, (fft_size / 2 + 31) / 32 * 32));
@@ -494,6 +788,13 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
     SB_CHECK_ARG(d_x && d_out && d_cp && d_in_off && rows >= 0 && num_symbols > 0 && fft_size > 0 && fft_size <= 8192,
                  "sb_ofdm_demodulate: bad arguments");
     if (rows == 0) return SB_OK;
+    if (fft_size <= kSmallFftMax) {
+        int rc = launch_fft_small<1>((const float2*)d_x, (float2*)d_out, fft_size, num_symbols, d_cp, d_in_off, in_len,
+                                     l_min, rows, shift, (cudaStream_t)stream);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        return SB_OK;
+    }
     FftPlan plan;
     SB_CHECK_ARG(make_plan(fft_size, &plan) == 0, "sb_ofdm_demodulate: fft_size has too many factors");
     int threads = std::min(256, std::max(32, (fft_size / 2 + 31) / 32 * 32));
@@ -727,6 +1028,17 @@ extern "C" int sb_ofdm_lmmse(const float* d_y, const float* d_h_hat, const float
     p.des = d_desired; p.und = d_undesired; p.out_ts = d_out_stream; p.data_pos = d_data_pos;
     p.xh = (float2*)d_x_hat; p.ne = d_no_eff; p.B = batch; p.RX = num_rx; p.ANT = num_rx_ant; p.TXS = num_tx_streams;
     p.S = num_symbols; p.F = num_subcarriers; p.K = streams_per_rx; p.KU = interferers_per_rx; p.ND = num_data;
+    long long total_re = batch * num_rx * (long long)num_symbols * num_subcarriers;
+    if (interferers_per_rx == 0 && streams_per_rx <= 4) {     // diagonal noise covariance: register kernel
+        switch (streams_per_rx) {
+            case 1: launch_lmmse_diag<1>(p, total_re, (cudaStream_t)stream); break;
+            case 2: launch_lmmse_diag<2>(p, total_re, (cudaStream_t)stream); break;
+            case 3: launch_lmmse_diag<3>(p, total_re, (cudaStream_t)stream); break;
+            default: launch_lmmse_diag<4>(p, total_re, (cudaStream_t)stream); break;
+        }
+        SB_LAUNCH_CHECK();
+        return SB_OK;
+    }
     size_t smem = 0;
     int threads = lmmse_threads(num_rx_ant, streams_per_rx, &smem);
     if (!threads) { sb_set_error("sb_ofdm_lmmse: %d receive antennas too many for the per-thread shared-memory path", num_rx_ant); return SB_EUNSUPPORTED; }

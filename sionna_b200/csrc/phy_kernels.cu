@@ -9,6 +9,7 @@
 // CPU oracle reproduces LLRs bit for bit.
 #include "sb_common.h"
 #include "sb_math.h"
+#include "sb_math2.cuh"
 #include "rng.cuh"
 
 namespace {
@@ -64,69 +65,222 @@ __device__ __forceinline__ float softplusf(float x) {
 }
 __device__ __forceinline__ float log_sigmoidf(float x) { return -softplusf(-x); }
 
-// One thread per symbol. exponents e_j = -|y - c_j|^2 / max(no, tiny) (+ prior term), then for every bit i:
-// app: logsumexp over points with bit i = 1 minus the same over bit i = 0; maxlog: max instead.
-template <int METHOD>   // 0 = app, 1 = maxlog
-__global__ void demap_kernel(const float2* __restrict__ y, const float* __restrict__ no, long long no_inner,
-                             const float2* __restrict__ points, int m, const float* __restrict__ prior,
-                             long long prior_inner, float* __restrict__ llr, long long n_sym, int hard_out) {
+// One thread per symbol, M = bits per symbol at compile time. Exponents e_j = -|y - c_j|^2 / max(no, tiny) (+ prior
+// term) are evaluated once per pass and feed all 2M groups {points with bit i = v} at the same time:
+//   pass 1: group maxima (maxlog: done);  pass 2 (app): sum_j exp(e_j - max_group) per group, two groups per packed
+//   FP32x2 exp (sb_math2.cuh, bit-identical to sb_expf); LLR_i = logsumexp(bit i = 1) - logsumexp(bit i = 0).
+// Per group the operation order is the one of tf.reduce_logsumexp over the points in ascending label order, which is
+// what the CPU oracle (oracle/mapping_ref.c) evaluates. The M LLRs of a warp's 32 symbols are staged through shared
+// memory so that global stores are contiguous.
+template <int M>
+__device__ __forceinline__ float demap_exponent(float2 yy, float2 c, float n0, const float* ls1, const float* ls0, int j,
+                                                bool with_prior) {
+    float dr = __fsub_rn(yy.x, c.x), di = __fsub_rn(yy.y, c.y);
+    float a = __fsqrt_rn(__fmaf_rn(dr, dr, __fmul_rn(di, di)));     // |y - c|  (tf.abs)
+    float e = __fdiv_rn(-__fmul_rn(a, a), n0);                       // -|.|^2 / no
+    if (with_prior) {
+        float ps = 0.f;
+#pragma unroll
+        for (int k = 0; k < M; ++k) ps = __fadd_rn(ps, ((j >> (M - 1 - k)) & 1) ? ls1[k] : ls0[k]);
+        e = __fadd_rn(ps, e);
+    }
+    return e;
+}
+
+template <int METHOD, int M>   // METHOD 0 = app, 1 = maxlog
+__global__ void __launch_bounds__(128) demap_kernel(const float2* __restrict__ y, const float* __restrict__ no,
+                                                    long long no_inner, const float2* __restrict__ points,
+                                                    const float* __restrict__ prior, long long prior_inner,
+                                                    float* __restrict__ llr, long long n_sym, int hard_out) {
     extern __shared__ float2 s_pts[];
-    const int npts = 1 << m;
-    for (int i = threadIdx.x; i < npts; i += blockDim.x) s_pts[i] = points[i];
+    constexpr int NPTS = 1 << M;
+    float* s_out = reinterpret_cast<float*>(s_pts + NPTS);          // [blockDim.x * M] staging for coalesced stores
+    for (int i = threadIdx.x; i < NPTS; i += blockDim.x) s_pts[i] = points[i];
     __syncthreads();
     const float tiny = 1.17549435e-38f;   // np.finfo(float32).tiny (mapping.py:653)
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_sym; s += stride) {
-        float2 yy = y[s];
-        float n0 = fmaxf(no[s / no_inner], tiny);
-        const float* pr = prior ? prior + (s / prior_inner) * m : nullptr;
-        for (int i = 0; i < m; ++i) {
-            const int bitmask = 1 << (m - 1 - i);          // label bit i, MSB first (mapping.py:894-907)
-            float acc[2];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_sym; base += stride) {
+        const long long s = base + threadIdx.x;
+        float out[M];
+        if (s < n_sym) {
+            const float2 yy = y[s];
+            const float n0 = fmaxf(no[s / no_inner], tiny);
+            float ls1[M], ls0[M];
+            const bool with_prior = prior != nullptr;
+            if (with_prior) {
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                float mx = -INFINITY;
-                // pass 1: maximum of the exponents over the subset
-                for (int j = 0; j < npts; ++j) {
-                    if (((j & bitmask) != 0) != (v == 1)) continue;
-                    float dr = __fsub_rn(yy.x, s_pts[j].x), di = __fsub_rn(yy.y, s_pts[j].y);
-                    float a = __fsqrt_rn(__fmaf_rn(dr, dr, __fmul_rn(di, di)));     // |y - c|  (tf.abs)
-                    float e = __fdiv_rn(-__fmul_rn(a, a), n0);                       // -|.|^2 / no
-                    if (pr) {
-                        float ps = 0.f;
-                        for (int k = 0; k < m; ++k) {
-                            float lab = ((j >> (m - 1 - k)) & 1) ? 1.f : -1.f;
-                            ps = __fadd_rn(ps, log_sigmoidf(__fmul_rn(lab, pr[k])));
-                        }
-                        e = __fadd_rn(ps, e);
-                    }
-                    mx = fmaxf(mx, e);
+                for (int k = 0; k < M; ++k) {
+                    float pk = prior[(s / prior_inner) * M + k];
+                    ls1[k] = log_sigmoidf(pk);                       // label bit 1 -> +prior
+                    ls0[k] = log_sigmoidf(__fmul_rn(-1.f, pk));
                 }
-                if (METHOD == 1) { acc[v] = mx; continue; }
-                // tf.reduce_logsumexp: log(sum(exp(x - max))) + max, max replaced by 0 if not finite
-                float mm = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
-                float sum = 0.f;
-                for (int j = 0; j < npts; ++j) {
-                    if (((j & bitmask) != 0) != (v == 1)) continue;
-                    float dr = __fsub_rn(yy.x, s_pts[j].x), di = __fsub_rn(yy.y, s_pts[j].y);
-                    float a = __fsqrt_rn(__fmaf_rn(dr, dr, __fmul_rn(di, di)));
-                    float e = __fdiv_rn(-__fmul_rn(a, a), n0);
-                    if (pr) {
-                        float ps = 0.f;
-                        for (int k = 0; k < m; ++k) {
-                            float lab = ((j >> (m - 1 - k)) & 1) ? 1.f : -1.f;
-                            ps = __fadd_rn(ps, log_sigmoidf(__fmul_rn(lab, pr[k])));
-                        }
-                        e = __fadd_rn(ps, e);
-                    }
-                    sum = __fadd_rn(sum, sb_expf(__fsub_rn(e, mm)));
-                }
-                acc[v] = __fadd_rn(sum > 0.f ? sb_logf(sum) : -INFINITY, mm);
             }
-            float l = __fsub_rn(acc[1], acc[0]);
-            llr[s * m + i] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;     // hard_decisions: utils/misc.py:270
+            float mx0[M], mx1[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) { mx0[i] = -INFINITY; mx1[i] = -INFINITY; }
+#pragma unroll 4
+            for (int j = 0; j < NPTS; ++j) {
+                const float e = demap_exponent<M>(yy, s_pts[j], n0, ls1, ls0, j, with_prior);
+#pragma unroll
+                for (int i = 0; i < M; ++i) {                        // label bit i, MSB first (mapping.py:894-907)
+                    if ((j >> (M - 1 - i)) & 1) mx1[i] = fmaxf(mx1[i], e);
+                    else mx0[i] = fmaxf(mx0[i], e);
+                }
+            }
+            if (METHOD == 1) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) out[i] = __fsub_rn(mx1[i], mx0[i]);
+            } else {
+                // tf.reduce_logsumexp: log(sum(exp(x - max))) + max, max replaced by 0 if not finite
+                float sm0[M], sm1[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    mx0[i] = (mx0[i] > -INFINITY && mx0[i] < INFINITY) ? mx0[i] : 0.f;
+                    mx1[i] = (mx1[i] > -INFINITY && mx1[i] < INFINITY) ? mx1[i] : 0.f;
+                    sm0[i] = 0.f; sm1[i] = 0.f;
+                }
+#pragma unroll 2
+                for (int j = 0; j < NPTS; ++j) {
+                    const float e = demap_exponent<M>(yy, s_pts[j], n0, ls1, ls0, j, with_prior);
+                    float t[M + 1];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) t[i] = __fsub_rn(e, ((j >> (M - 1 - i)) & 1) ? mx1[i] : mx0[i]);
+                    t[M] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < M; i += 2) {                 // exp of two groups at a time (FFMA2)
+                        float2 a = make_float2(fmaxf(t[i], -87.3f), fmaxf(t[i + 1], -87.3f));
+                        float2 r = sb_expf2_inrange(a);
+                        if (t[i] < -87.3f) r.x = 0.f;                // sb_expf: exact 0 below -87.3
+                        if (t[i + 1] < -87.3f) r.y = 0.f;
+                        t[i] = r.x;
+                        t[i + 1] = r.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        if ((j >> (M - 1 - i)) & 1) sm1[i] = __fadd_rn(sm1[i], t[i]);
+                        else sm0[i] = __fadd_rn(sm0[i], t[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    float a1 = __fadd_rn(sm1[i] > 0.f ? sb_logf(sm1[i]) : -INFINITY, mx1[i]);
+                    float a0 = __fadd_rn(sm0[i] > 0.f ? sb_logf(sm0[i]) : -INFINITY, mx0[i]);
+                    out[i] = __fsub_rn(a1, a0);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) out[i] = hard_out ? (out[i] > 0.f ? 1.f : 0.f) : out[i];   // utils/misc.py:270
         }
+        __syncthreads();                                            // previous tile's copy-out has finished
+        if (s < n_sym) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) s_out[threadIdx.x * M + i] = out[i];
+        }
+        __syncthreads();
+        const long long rem = n_sym - base;
+        const int cnt = (int)((rem < (long long)blockDim.x ? rem : (long long)blockDim.x) * M);
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) llr[base * M + e] = s_out[e];
     }
+}
+
+// Separable constellations (every square QAM of mapping.py:104-117: even label bits select the real PAM level, odd
+// label bits the imaginary one): the 2-D sums factor, exp(e_j) = exp(e_re) exp(e_im), and the factor of the other
+// dimension cancels in the LLR, so bit i only needs the 2^(M/2) exponents of its own dimension:
+//   LLR_(2u+d) = logsumexp_{t: bit u of t = 1} e_d(t) - logsumexp_{t: bit u = 0} e_d(t),  e_d(t) = -(y_d - a_d(t))^2 * (1/no)
+// (max instead of logsumexp for maxlog). 2 * 2^(M/2) exponents instead of 2^M and M * 2^(M/2) instead of M * 2^M
+// exp() per symbol. Same value as the generic kernel up to fp32 rounding (tests: rtol 1e-4 against the oracle).
+template <int METHOD, int H>   // H = M / 2 bits per dimension
+__global__ void __launch_bounds__(128) demap_qam_kernel(const float2* __restrict__ y, const float* __restrict__ no,
+                                                        long long no_inner, const float* __restrict__ lev_re,
+                                                        const float* __restrict__ lev_im, float* __restrict__ llr,
+                                                        long long n_sym, int hard_out) {
+    constexpr int L = 1 << H, M = 2 * H;
+    extern __shared__ float s_out_q[];                              // [blockDim.x * M]
+    float lr[L], li[L];
+#pragma unroll
+    for (int t = 0; t < L; ++t) { lr[t] = lev_re[t]; li[t] = lev_im[t]; }
+    const float tiny = 1.17549435e-38f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_sym; base += stride) {
+        const long long s = base + threadIdx.x;
+        float out[M];
+        if (s < n_sym) {
+            const float2 yy = y[s];
+            const float inv_n0 = __fdiv_rn(1.0f, fmaxf(no[s / no_inner], tiny));   // one division per symbol
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const float yd = d ? yy.y : yy.x;
+                float e[L];
+#pragma unroll
+                for (int t = 0; t < L; ++t) {
+                    float dd = __fsub_rn(yd, d ? li[t] : lr[t]);
+                    e[t] = __fmul_rn(-__fmul_rn(dd, dd), inv_n0);
+                }
+#pragma unroll
+                for (int u = 0; u < H; ++u) {
+                    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                    for (int t = 0; t < L; ++t) {
+                        if ((t >> (H - 1 - u)) & 1) mx1 = fmaxf(mx1, e[t]);
+                        else mx0 = fmaxf(mx0, e[t]);
+                    }
+                    float l;
+                    if (METHOD == 1) {
+                        l = __fsub_rn(mx1, mx0);
+                    } else {
+                        mx0 = (mx0 > -INFINITY && mx0 < INFINITY) ? mx0 : 0.f;
+                        mx1 = (mx1 > -INFINITY && mx1 < INFINITY) ? mx1 : 0.f;
+                        float s0 = 0.f, s1 = 0.f;
+                        // the k-th member of group 0 and of group 1 share one packed exp
+#pragma unroll
+                        for (int k = 0; k < L / 2; ++k) {
+                            const int lo = k & ((1 << (H - 1 - u)) - 1), hi = k >> (H - 1 - u);
+                            const int t0 = (hi << (H - u)) | lo, t1 = t0 | (1 << (H - 1 - u));
+                            float a0 = __fsub_rn(e[t0], mx0), a1 = __fsub_rn(e[t1], mx1);
+                            float2 r = sb_expf2_inrange(make_float2(fmaxf(a0, -87.3f), fmaxf(a1, -87.3f)));
+                            if (a0 < -87.3f) r.x = 0.f;
+                            if (a1 < -87.3f) r.y = 0.f;
+                            s0 = __fadd_rn(s0, r.x);
+                            s1 = __fadd_rn(s1, r.y);
+                        }
+                        float b1 = __fadd_rn(s1 > 0.f ? sb_logf(s1) : -INFINITY, mx1);
+                        float b0 = __fadd_rn(s0 > 0.f ? sb_logf(s0) : -INFINITY, mx0);
+                        l = __fsub_rn(b1, b0);
+                    }
+                    out[2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
+                }
+            }
+        }
+        __syncthreads();
+        if (s < n_sym) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) s_out_q[threadIdx.x * M + i] = out[i];
+        }
+        __syncthreads();
+        const long long rem = n_sym - base;
+        const int cnt = (int)((rem < (long long)blockDim.x ? rem : (long long)blockDim.x) * M);
+        for (int q = threadIdx.x; q < cnt; q += blockDim.x) llr[base * M + q] = s_out_q[q];
+    }
+}
+
+template <int METHOD>
+void launch_demap_qam(int h, int grid, cudaStream_t st, const float2* y, const float* no, long long no_inner,
+                      const float* lev_re, const float* lev_im, float* llr, long long n_sym, int hard_out) {
+    const size_t smem = sizeof(float) * 128 * 2 * h;
+#define SB_QAM_CASE(HH) case HH: demap_qam_kernel<METHOD, HH><<<grid, 128, smem, st>>>(y, no, no_inner, lev_re, lev_im, llr, n_sym, hard_out); break;
+    switch (h) { SB_QAM_CASE(1) SB_QAM_CASE(2) SB_QAM_CASE(3) SB_QAM_CASE(4) SB_QAM_CASE(5) }
+#undef SB_QAM_CASE
+}
+
+template <int METHOD>
+void launch_demap(int m, int grid, size_t smem, cudaStream_t st, const float2* y, const float* no, long long no_inner,
+                  const float2* pts, const float* prior, long long prior_inner, float* llr, long long n_sym, int hard_out) {
+#define SB_DEMAP_CASE(MM) case MM: demap_kernel<METHOD, MM><<<grid, 128, smem, st>>>(y, no, no_inner, pts, prior, prior_inner, llr, n_sym, hard_out); break;
+    switch (m) {
+        SB_DEMAP_CASE(1) SB_DEMAP_CASE(2) SB_DEMAP_CASE(3) SB_DEMAP_CASE(4) SB_DEMAP_CASE(5) SB_DEMAP_CASE(6)
+        SB_DEMAP_CASE(7) SB_DEMAP_CASE(8) SB_DEMAP_CASE(9) SB_DEMAP_CASE(10) SB_DEMAP_CASE(11) SB_DEMAP_CASE(12)
+    }
+#undef SB_DEMAP_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -272,14 +426,31 @@ extern "C" int sb_demap(const float* d_y, const float* d_no, int64_t no_inner, c
     SB_CHECK_ARG(method == 0 || method == 1, "sb_demap: method must be 0 (app) or 1 (maxlog)");
     SB_CHECK_ARG(!d_prior || prior_inner >= 1, "sb_demap: prior_inner must be >= 1");
     if (n_sym == 0) return SB_OK;
-    size_t smem = sizeof(float2) << m;
+    size_t smem = (sizeof(float2) << m) + sizeof(float) * 128 * m;
     int grid = grid_for(n_sym, 128);
     if (method == 0)
-        demap_kernel<0><<<grid, 128, smem, (cudaStream_t)stream>>>((const float2*)d_y, d_no, no_inner, (const float2*)d_points,
-                                                                  m, d_prior, prior_inner, d_llr, n_sym, hard_out);
+        launch_demap<0>(m, grid, smem, (cudaStream_t)stream, (const float2*)d_y, d_no, no_inner, (const float2*)d_points,
+                        d_prior, prior_inner, d_llr, n_sym, hard_out);
     else
-        demap_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>((const float2*)d_y, d_no, no_inner, (const float2*)d_points,
-                                                                  m, d_prior, prior_inner, d_llr, n_sym, hard_out);
+        launch_demap<1>(m, grid, smem, (cudaStream_t)stream, (const float2*)d_y, d_no, no_inner, (const float2*)d_points,
+                        d_prior, prior_inner, d_llr, n_sym, hard_out);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_demap_qam(const float* d_y, const float* d_no, int64_t no_inner, const float* d_levels_re,
+                            const float* d_levels_im, int32_t m, int32_t method, float* d_llr, int64_t n_sym,
+                            int32_t hard_out, void* stream) {
+    if (n_sym == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
+    SB_CHECK_ARG(d_y && d_no && d_levels_re && d_levels_im && d_llr && m >= 2 && m <= 10 && m % 2 == 0 && no_inner >= 1 &&
+                     (method == 0 || method == 1), "sb_demap_qam: bad arguments (m even, 2..10; method 0 | 1)");
+    int grid = grid_for(n_sym, 128);
+    if (method == 0)
+        launch_demap_qam<0>(m / 2, grid, (cudaStream_t)stream, (const float2*)d_y, d_no, no_inner, d_levels_re, d_levels_im,
+                            d_llr, n_sym, hard_out);
+    else
+        launch_demap_qam<1>(m / 2, grid, (cudaStream_t)stream, (const float2*)d_y, d_no, no_inner, d_levels_re, d_levels_im,
+                            d_llr, n_sym, hard_out);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -270,9 +270,38 @@ class Demapper(Block):
             else:
                 pr_t, pr_inner = p.expand(list(y.shape) + [m]).contiguous().reshape(-1), 1
         llr = torch.empty(list(y.shape[:-1]) + [y.shape[-1] * m], dtype=torch.float32, device=dev)
-        check(lib().sb_demap(ptr(y), ptr(no_t), no_inner, ptr(self._constellation()), m, self._method, ptr(pr_t),
+        pts = self._constellation()
+        levels = self._separable_levels(pts) if prior is None else None
+        if levels is not None:                                  # square QAM: per-dimension kernel
+            check(lib().sb_demap_qam(ptr(y), ptr(no_t), no_inner, ptr(levels[0]), ptr(levels[1]), m, self._method,
+                                     ptr(llr), n_sym, int(self._hard_out), current_stream()), "sb_demap_qam")
+            return llr
+        check(lib().sb_demap(ptr(y), ptr(no_t), no_inner, ptr(pts), m, self._method, ptr(pr_t),
                              pr_inner, ptr(llr), n_sym, int(self._hard_out), current_stream()), "sb_demap")
         return llr
+
+    def _separable_levels(self, pts):
+        """Device tensors (levels_re, levels_im) if every point equals levels_re[even label bits] + 1j * levels_im[odd
+        label bits] exactly (all square QAMs, mapping.py:104-117), else None. Cached per constellation tensor."""
+        key = (pts.data_ptr(), pts._version, pts.device)
+        if getattr(self, "_sep_key", None) == key:
+            return self._sep_val
+        p = pts.detach().cpu().numpy()
+        m = self._constellation.num_bits_per_symbol
+        val = None
+        if m % 2 == 0 and 2 <= m <= 10:
+            h = m // 2
+            j = np.arange(len(p))
+            bits = (j[:, None] >> np.arange(m - 1, -1, -1)) & 1
+            w = 1 << np.arange(h - 1, -1, -1)
+            jr, ji = bits[:, 0::2] @ w, bits[:, 1::2] @ w
+            lev_re, lev_im = np.zeros(1 << h, np.float32), np.zeros(1 << h, np.float32)
+            lev_re[jr[ji == 0]] = p.real[ji == 0]
+            lev_im[ji[jr == 0]] = p.imag[jr == 0]
+            if np.array_equal(lev_re[jr], p.real.astype(np.float32)) and np.array_equal(lev_im[ji], p.imag.astype(np.float32)):
+                val = (torch.from_numpy(lev_re).to(pts.device), torch.from_numpy(lev_im).to(pts.device))
+        self._sep_key, self._sep_val = key, val
+        return val
 
 
 class BinarySource(Block):
