@@ -340,27 +340,30 @@ __global__ void interp_lin_kernel(const float2* __restrict__ h, const int* __res
                                   const int* __restrict__ fy0, const int* __restrict__ fy1, const int* __restrict__ ty0,
                                   const int* __restrict__ ty1, const int* __restrict__ npil, int time_avg,
                                   float2* __restrict__ out, long long B, int TS, int S, int F, int P) {
-    const long long total = B * TS * (long long)S * F;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int f = (int)(i % F);
-        int sidx = (int)((i / F) % S);
-        int ts = (int)((i / ((long long)F * S)) % TS);
-        long long b = i / ((long long)F * S * TS);
-        const float2* hp = h + (b * TS + ts) * (long long)P;
-        const int base = ts * S * F;
-        float2 v;
-        if (time_avg) {
-            float2 acc = make_float2(0.f, 0.f);
-            for (int s2 = 0; s2 < S; ++s2) acc = cadd(acc, freq_interp(hp, fx0, fx1, fy0, fy1, base + s2 * F + f, f));
-            float n = (float)npil[ts];
-            v = make_float2(acc.x / n, acc.y / n);   // every symbol then carries the average: time interpolation is flat
-        } else {
-            int s0 = ty0[ts * S + sidx], s1 = ty1[ts * S + sidx];
-            float2 y0 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s0 * F + f, f);
-            float2 y1 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s1 * F + f, f);
-            v = lerp_c((float)sidx, (float)s0, (float)s1, y0, y1);
+    // one (batch', stream) row of S*F outputs per loop trip of a CTA: all index arithmetic stays 32-bit
+    const int SF = S * F;
+    const long long rows = B * TS;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int ts = (int)(row % TS);
+        const float2* hp = h + row * (long long)P;
+        float2* op = out + row * (long long)SF;
+        const int base = ts * SF;
+        for (int e = threadIdx.x; e < SF; e += blockDim.x) {
+            const int sidx = e / F, f = e - sidx * F;
+            float2 v;
+            if (time_avg) {
+                float2 acc = make_float2(0.f, 0.f);
+                for (int s2 = 0; s2 < S; ++s2) acc = cadd(acc, freq_interp(hp, fx0, fx1, fy0, fy1, base + s2 * F + f, f));
+                float n = (float)npil[ts];
+                v = make_float2(acc.x / n, acc.y / n);   // every symbol then carries the average: time interpolation is flat
+            } else {
+                int s0 = ty0[ts * S + sidx], s1 = ty1[ts * S + sidx];
+                float2 y0 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s0 * F + f, f);
+                float2 y1 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s1 * F + f, f);
+                v = lerp_c((float)sidx, (float)s0, (float)s1, y0, y1);
+            }
+            op[e] = v;
         }
-        out[i] = v;
     }
 }
 
@@ -566,7 +569,7 @@ __global__ void ofdm_lmmse_kernel(const OfdmEqParams p) {
 // then A = B + I = C C^H, A^-1 = C^-H C^-1 and, without forming G = A^-1 H_w^H (K x M),
 //   G y_w = A^-1 z,   diag(G H_w)_k = sum_j (A^-1)_kj B_jk          (same quantities as lmmse_core)
 template <int K>
-__global__ void __launch_bounds__(128) ofdm_lmmse_diag_kernel(const OfdmEqParams p) {
+__global__ void __launch_bounds__(128, 6) ofdm_lmmse_diag_kernel(const OfdmEqParams p) {
     const long long SF = (long long)p.S * p.F;
     const long long total = p.B * p.RX * SF;
     const int M = p.ANT;
@@ -862,7 +865,9 @@ extern "C" int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32
                  "sb_interp_lin: bad arguments");
     long long total = batch * num_streams * (long long)num_symbols * num_subcarriers;
     if (total == 0) return SB_OK;
-    interp_lin_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const long long rows_il = batch * num_streams;
+    const int grid_il = (int)std::min<long long>(rows_il, (long long)sb_num_sms() * 16);
+    interp_lin_kernel<<<grid_il, 256, 0, (cudaStream_t)stream>>>(
         (const float2*)d_h, d_fx0, d_fx1, d_fy0, d_fy1, d_ty0, d_ty1, d_npil, time_avg, (float2*)d_out, batch, num_streams,
         num_symbols, num_subcarriers, num_pilots);
     SB_LAUNCH_CHECK();

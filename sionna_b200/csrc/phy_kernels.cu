@@ -251,15 +251,20 @@ __global__ void __launch_bounds__(128) demap_qam_kernel(const float2* __restrict
                 }
             }
         }
-        __syncthreads();
-        if (s < n_sym) {
+        // stage the warp's 32 x M LLRs through its own shared-memory tile: contiguous global stores, no CTA barrier
+        {
+            const int lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 32 * M;
+            __syncwarp();                                           // previous tile's copy-out has finished
+            if (s < n_sym) {
 #pragma unroll
-            for (int i = 0; i < M; ++i) s_out_q[threadIdx.x * M + i] = out[i];
+                for (int i = 0; i < M; ++i) s_out_q[wbase + lane * M + i] = out[i];
+            }
+            __syncwarp();
+            const long long wfirst = base + (threadIdx.x & ~31);
+            const long long rem = n_sym - wfirst;
+            const int cnt = rem <= 0 ? 0 : (int)((rem < 32 ? rem : 32) * M);
+            for (int q = lane; q < cnt; q += 32) llr[wfirst * M + q] = s_out_q[wbase + q];
         }
-        __syncthreads();
-        const long long rem = n_sym - base;
-        const int cnt = (int)((rem < (long long)blockDim.x ? rem : (long long)blockDim.x) * M);
-        for (int q = threadIdx.x; q < cnt; q += blockDim.x) llr[base * M + q] = s_out_q[q];
     }
 }
 
