@@ -196,11 +196,12 @@ int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, const float* d
                     int64_t no_inner, float* d_h, float* d_err, int64_t batch, int32_t num_streams, int32_t num_pilots,
                     int32_t grid_size, void* stream);
 /* LinearInterpolator._interpolate (ofdm/channel_estimation.py:657-734) with the index tables of :522-655:
- * d_h [batch, num_streams, num_pilots] -> d_out [batch, num_streams, num_symbols, num_subcarriers]. */
+ * d_h [batch, num_streams, num_pilots] -> d_out [batch, num_streams, num_symbols, num_subcarriers]; words = 2:
+ * complex64 values (channel estimates), words = 1: fp32 values (error variances). */
 int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, const int32_t* d_fy0,
                   const int32_t* d_fy1, const int32_t* d_ty0, const int32_t* d_ty1, const int32_t* d_npil,
                   int32_t time_avg, float* d_out, int64_t batch, int32_t num_streams, int32_t num_symbols,
-                  int32_t num_subcarriers, int32_t num_pilots, void* stream);
+                  int32_t num_subcarriers, int32_t num_pilots, int32_t words, void* stream);
 /* ApplyOFDMChannel.call (channel/apply_ofdm_channel.py:70-80): y[b, r, re] = sum_t h[b, r, t, re] x[b, t, re] + w,
  * r over rx antennas, t over tx antennas, w ~ CN(0, no) if add_noise. */
 int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,

@@ -46,7 +46,7 @@ SIGNATURES = {
     "sb_gather_rows": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "sb_rg_map": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "sb_ls_at_pilots": (i32, [vp, vp, vp, vp, i64, vp, vp, i64, i32, i32, i32, vp]),
-    "sb_interp_lin": (i32, [vp] * 8 + [i32, vp, i64, i32, i32, i32, i32, vp]),
+    "sb_interp_lin": (i32, [vp] * 8 + [i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "sb_apply_ofdm_channel": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, u64, u64, vp]),
     "sb_pusch_precode": (i32, [vp, vp, vp, i64, i32, i32, i32, i64, vp]),
     "sb_pusch_ls_combine": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),

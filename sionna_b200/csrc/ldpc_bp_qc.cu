@@ -45,7 +45,7 @@ struct QcParams {
     float* state_out;
     long long B;
     int num_iter, hard_out, use_tma;
-    int tab_rep;             // copies of the phi log table in shared memory (32 or 1; 0: rule does not use it)
+    int tab_rep;             // copies of the phi log table in shared memory (32, 8 or 1; 0: rule does not use it)
     float offset, llr_max;
 };
 
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
             tab[SB_LOGTAB_N * REP + i] = sb_logtab_dev[2 * (i / REP) + 1];
         }
         lt.inv = msgb + off_tab;
-        lt.lane_off = REP == 32 ? 4 * lane : 0;
+        lt.lane_off = 4 * (lane & (REP - 1));
     }
     if (p.use_tma && tid == 0) {
         mbar_init(bar, 1);
@@ -582,6 +582,7 @@ template <int RULE>
 int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
     auto kern = ldpc_bp_qc_kernel<RULE, 32>;
     if constexpr (RULE == SB_CN_BOXPLUS_PHI) {
+        if (p.tab_rep == 8) kern = ldpc_bp_qc_kernel<RULE, 8>;
         if (p.tab_rep == 1) kern = ldpc_bp_qc_kernel<RULE, 1>;
     }
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -759,6 +760,7 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     if (!g->qc || !g->flooding || vn_rule != SB_VN_SUM || d_state_in || cn_rule > SB_CN_OFFSET_MINSUM) return SB_OK;
     // boxplus-phi keeps the log table of phi in shared memory: one copy per bank pair if it fits, else a single copy
     int tab_rep = cn_rule == SB_CN_BOXPLUS_PHI ? 32 : 0;
+    if (tab_rep && qc_smem_bytes(g, tab_rep) > (size_t)g->smem_optin) tab_rep = 8;
     if (tab_rep && qc_smem_bytes(g, tab_rep) > (size_t)g->smem_optin) tab_rep = 1;
     const size_t smem = qc_smem_bytes(g, tab_rep);
     if (smem > (size_t)g->smem_optin) return SB_OK;

@@ -329,40 +329,58 @@ __device__ __forceinline__ float2 lerp_c(float x, float x0, float x1, float2 y0,
     float t = x - x0;
     return make_float2(t * slope.x + y0.x, t * slope.y + y0.y);
 }
-__device__ __forceinline__ float2 freq_interp(const float2* hp, const int* fx0, const int* fx1, const int* fy0,
-                                              const int* fy1, int idx, int f) {
+__device__ __forceinline__ float lerp_c(float x, float x0, float x1, float y0, float y1) {
+    float dx = x1 - x0;
+    float slope = dx == 0.f ? 0.f : (y1 - y0) / dx;
+    return (x - x0) * slope + y0;
+}
+__device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return cadd(a, b); }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 vdiv(float2 a, float n) { return make_float2(a.x / n, a.y / n); }
+__device__ __forceinline__ float vdiv(float a, float n) { return a / n; }
+
+template <typename T>
+__device__ __forceinline__ T freq_interp(const T* hp, const int* fx0, const int* fx1, const int* fy0, const int* fy1, int idx,
+                                         int f) {
     int i0 = fy0[idx], i1 = fy1[idx];
-    float2 y0 = i0 > 0 ? hp[i0 - 1] : make_float2(0.f, 0.f);
-    float2 y1 = i1 > 0 ? hp[i1 - 1] : make_float2(0.f, 0.f);
+    T y0 = i0 > 0 ? hp[i0 - 1] : vzero(T());
+    T y1 = i1 > 0 ? hp[i1 - 1] : vzero(T());
     return lerp_c((float)f, (float)fx0[idx], (float)fx1[idx], y0, y1);
 }
-__global__ void interp_lin_kernel(const float2* __restrict__ h, const int* __restrict__ fx0, const int* __restrict__ fx1,
+// T = float2 (channel estimates) or float (error variances). A CTA owns (batch', stream) rows; a thread owns one
+// subcarrier column f of the row and walks the OFDM symbols: the two frequency-interpolated values y(s0, f), y(s1, f) a
+// symbol interpolates between are re-evaluated only when (s0, s1) changes (once or twice per slot), so an output costs
+// two table words + one lerp; stores are contiguous over f.
+template <typename T>
+__global__ void interp_lin_kernel(const T* __restrict__ h, const int* __restrict__ fx0, const int* __restrict__ fx1,
                                   const int* __restrict__ fy0, const int* __restrict__ fy1, const int* __restrict__ ty0,
                                   const int* __restrict__ ty1, const int* __restrict__ npil, int time_avg,
-                                  float2* __restrict__ out, long long B, int TS, int S, int F, int P) {
-    // one (batch', stream) row of S*F outputs per loop trip of a CTA: all index arithmetic stays 32-bit
+                                  T* __restrict__ out, long long B, int TS, int S, int F, int P) {
     const int SF = S * F;
     const long long rows = B * TS;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int ts = (int)(row % TS);
-        const float2* hp = h + row * (long long)P;
-        float2* op = out + row * (long long)SF;
+        const T* hp = h + row * (long long)P;
+        T* op = out + row * (long long)SF;
         const int base = ts * SF;
-        for (int e = threadIdx.x; e < SF; e += blockDim.x) {
-            const int sidx = e / F, f = e - sidx * F;
-            float2 v;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
             if (time_avg) {
-                float2 acc = make_float2(0.f, 0.f);
-                for (int s2 = 0; s2 < S; ++s2) acc = cadd(acc, freq_interp(hp, fx0, fx1, fy0, fy1, base + s2 * F + f, f));
-                float n = (float)npil[ts];
-                v = make_float2(acc.x / n, acc.y / n);   // every symbol then carries the average: time interpolation is flat
+                T acc = vzero(T());
+                for (int s2 = 0; s2 < S; ++s2) acc = vadd(acc, freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s2 * F + f, f));
+                const T v = vdiv(acc, (float)npil[ts]);        // every symbol carries the average: time interpolation is flat
+                for (int s = 0; s < S; ++s) op[s * F + f] = v;
             } else {
-                int s0 = ty0[ts * S + sidx], s1 = ty1[ts * S + sidx];
-                float2 y0 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s0 * F + f, f);
-                float2 y1 = freq_interp(hp, fx0, fx1, fy0, fy1, base + s1 * F + f, f);
-                v = lerp_c((float)sidx, (float)s0, (float)s1, y0, y1);
+                int last0 = -1, last1 = -1;
+                T y0 = vzero(T()), y1 = vzero(T());
+                for (int s = 0; s < S; ++s) {
+                    const int s0 = ty0[ts * S + s], s1 = ty1[ts * S + s];
+                    if (s0 != last0) { y0 = freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s0 * F + f, f); last0 = s0; }
+                    if (s1 != last1) { y1 = freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s1 * F + f, f); last1 = s1; }
+                    op[s * F + f] = lerp_c((float)s, (float)s0, (float)s1, y0, y1);
+                }
             }
-            op[e] = v;
         }
     }
 }
@@ -859,17 +877,22 @@ extern "C" int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, con
 extern "C" int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, const int32_t* d_fy0,
                              const int32_t* d_fy1, const int32_t* d_ty0, const int32_t* d_ty1, const int32_t* d_npil,
                              int32_t time_avg, float* d_out, int64_t batch, int32_t num_streams, int32_t num_symbols,
-                             int32_t num_subcarriers, int32_t num_pilots, void* stream) {
+                             int32_t num_subcarriers, int32_t num_pilots, int32_t words, void* stream) {
     if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
-    SB_CHECK_ARG(d_h && d_fx0 && d_fx1 && d_fy0 && d_fy1 && d_ty0 && d_ty1 && d_npil && d_out && batch >= 0,
-                 "sb_interp_lin: bad arguments");
-    long long total = batch * num_streams * (long long)num_symbols * num_subcarriers;
-    if (total == 0) return SB_OK;
-    const long long rows_il = batch * num_streams;
-    const int grid_il = (int)std::min<long long>(rows_il, (long long)sb_num_sms() * 16);
-    interp_lin_kernel<<<grid_il, 256, 0, (cudaStream_t)stream>>>(
-        (const float2*)d_h, d_fx0, d_fx1, d_fy0, d_fy1, d_ty0, d_ty1, d_npil, time_avg, (float2*)d_out, batch, num_streams,
-        num_symbols, num_subcarriers, num_pilots);
+    SB_CHECK_ARG(d_h && d_fx0 && d_fx1 && d_fy0 && d_fy1 && d_ty0 && d_ty1 && d_npil && d_out && batch >= 0 &&
+                     (words == 1 || words == 2), "sb_interp_lin: bad arguments (words: 1 = real, 2 = complex)");
+    const long long rows = batch * num_streams;
+    if (rows == 0 || num_symbols * num_subcarriers == 0) return SB_OK;
+    const int grid = (int)std::min<long long>(rows, (long long)sb_num_sms() * 16);
+    const int threads = std::min(256, std::max(32, (num_subcarriers + 31) / 32 * 32));
+    if (words == 2)
+        interp_lin_kernel<float2><<<grid, threads, 0, (cudaStream_t)stream>>>(
+            (const float2*)d_h, d_fx0, d_fx1, d_fy0, d_fy1, d_ty0, d_ty1, d_npil, time_avg, (float2*)d_out, batch,
+            num_streams, num_symbols, num_subcarriers, num_pilots);
+    else
+        interp_lin_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(
+            d_h, d_fx0, d_fx1, d_fy0, d_fy1, d_ty0, d_ty1, d_npil, time_avg, d_out, batch, num_streams, num_symbols,
+            num_subcarriers, num_pilots);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

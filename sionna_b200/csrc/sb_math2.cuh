@@ -60,11 +60,12 @@ __device__ __forceinline__ float2 sb_logf2(float2 y) {
 // ((bits(y) >> rs) & mask) | lane_off of either array: the host picks the replication factor -- 32 copies (one per bank,
 // conflict-free LDS: rs 10, mask 0x1f80, lane_off 4*lane) when the table fits next to the messages, else a single copy
 // (rs 15, mask 0xfc, lane_off 0).
-template <int REP>                                        // REP = 32 or 1: compile-time shift, mask and array distance
+template <int REP>                                        // REP = 32, 8 or 1 copies: compile-time shift, mask, distance
 struct LogTab {
     uint32_t inv, lane_off;                               // `inv` is CTA-uniform; the log c array follows the inv_c array
-    static constexpr int rs = REP == 32 ? SB_LOGTAB_SHIFT - 7 : SB_LOGTAB_SHIFT - 2;
-    static constexpr int mask = (SB_LOGTAB_N - 1) << (REP == 32 ? 7 : 2);
+    static constexpr int log_stride = REP == 32 ? 7 : (REP == 8 ? 5 : 2);   // log2(REP * 4 bytes)
+    static constexpr int rs = SB_LOGTAB_SHIFT - log_stride;
+    static constexpr int mask = (SB_LOGTAB_N - 1) << log_stride;
     static constexpr int dist = SB_LOGTAB_N * REP * 4;
 };
 

@@ -131,18 +131,19 @@ class LinearInterpolator(BaseChannelInterpolator):
         if self._tabs is None or self._tabs[0].device != x.device:
             self._tabs = [torch.from_numpy(t).to(x.device) for t in self._tabs_np]
         lead = list(x.shape[:-3])
-        xin = _flat_ts(x.to(torch.complex64), ts)
+        cplx = x.is_complex()                                   # channel estimates: complex64, error variances: fp32
+        xin = _flat_ts(x.to(torch.complex64 if cplx else torch.float32), ts)
         b, p = xin.shape[0], xin.shape[-1]
-        out = torch.empty((b, ts, s_, f_), dtype=torch.complex64, device=x.device)
+        out = torch.empty((b, ts, s_, f_), dtype=xin.dtype, device=x.device)
         t = self._tabs
         check(lib().sb_interp_lin(ptr(xin), ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), ptr(t[4]), ptr(t[5]), ptr(t[6]),
-                                  int(self._time_avg), ptr(out), b, ts, s_, f_, p, current_stream()), "sb_interp_lin")
+                                  int(self._time_avg), ptr(out), b, ts, s_, f_, p, 2 if cplx else 1, current_stream()),
+              "sb_interp_lin")
         return out.reshape(lead + [tx, st, s_, f_])
 
     def __call__(self, h_hat, err_var):
-        h = self._interpolate(h_hat)
-        ev = self._interpolate(err_var.to(torch.complex64)).real.contiguous()     # :729-732
-        return h, ev
+        # the reference interpolates err_var as a complex tensor and keeps the real part (:729-732); same values in fp32
+        return self._interpolate(h_hat), self._interpolate(err_var)
 
 
 class BaseChannelEstimator(Block):

@@ -60,6 +60,22 @@ def test_generic_pcm_bit_exact(cuda_device, rule, pcm_id):
         assert np.all(x.cpu().numpy()[0] == 0.0)     # all-erasure in -> exactly 0 out (test_ldpc_decoding.py:277-290)
 
 
+@pytest.mark.parametrize("k,n", [(5032, 9216), (5032, 9600)])
+def test_qc_phi_with_reduced_log_table_copies(cuda_device, k, n):
+    """Graphs that leave < 16 KB of shared memory next to the messages run the boxplus-phi kernel with 8 copies
+    ((5032, 9216): the code block of a 16-PRB PUSCH slot) or a single copy ((5032, 9600)) of the log table: same bits."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    rng = np.random.default_rng(n)
+    enc_r = O.LDPC5GEncoderRef(k, n)
+    c = enc_r(rng.integers(0, 2, (12, k)))
+    llr = _noisy_llr(c, 1.2, k / n, rng)
+    dec = LDPC5GDecoder(LDPC5GEncoder(k, n), hard_out=False, return_infobits=False, num_iter=8)
+    assert dec._graph.is_qc()
+    x = dec(torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+    ref = O.LDPC5GDecoderRef(enc_r, hard_out=False, return_infobits=False, num_iter=8)
+    assert np.array_equal(x, ref(llr, math_mode=1, order="kernel"))
+
+
 @pytest.mark.parametrize("rule", RULES)
 @pytest.mark.parametrize("k,n", [(64, 128), (100, 200), (562, 871), (1024, 2048), (1500, 2000), (4224, 8448)])
 def test_5g_bit_exact(cuda_device, kernel_path, rule, k, n):
