@@ -40,6 +40,17 @@ __device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
     return make_float2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
 
+// Row-wise element kernels: blockDim = (tx, ty) with tx = row length rounded up to a warp (<= 256) and ty rows per CTA;
+// a CTA walks rows (64-bit row index once per row), threads walk columns with 32-bit arithmetic only.
+struct RowLaunch { dim3 block; int grid; };
+inline RowLaunch row_launch(long long rows, int cols) {
+    int tx = std::min(256, std::max(32, (cols + 31) / 32 * 32));
+    int ty = std::max(1, 256 / tx);
+    long long ctas = (rows + ty - 1) / ty;
+    int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sb_num_sms() * 16));
+    return RowLaunch{dim3((unsigned)tx, (unsigned)ty, 1), grid};
+}
+
 inline int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
     long long cap = (long long)sb_num_sms() * 16;
@@ -54,6 +65,7 @@ inline int grid_for(long long work_items, int threads) {
 struct FftPlan {
     int n, n_radix;
     int radix[24];
+    int span_shift[24];      // log2 of the stage's span (product of the previous radices) if it is a power of two, else -1
 };
 
 __device__ void fft_inplace_smem(float2* buf0, float2* buf1, const float2* W, const FftPlan& plan, float2** result) {
@@ -64,25 +76,28 @@ __device__ void fft_inplace_smem(float2* buf0, float2* buf1, const float2* W, co
     for (int st = 0; st < plan.n_radix; ++st) {
         const int p = plan.radix[st], m = n / p;
         const int wstep = N / p;                       // exp(-2 pi i r c / p) = W[(r*c mod p) * N/p]
+        const int sh = plan.span_shift[st];
         for (int b = tid; b < N / p; b += T) {         // butterfly (q, k): q in [0, s), k in [0, m)
-            const int q = b % s, k = b / s;
+            const int k = sh >= 0 ? (b >> sh) : b / s;
+            const int q = b - k * s;
+            // twiddle exponents c * k * s stay below N (k < m, c < p, p * m * s = N): no modulo needed
             if (p == 2) {
                 float2 a0 = x[q + s * k], a1 = x[q + s * (k + m)];
                 y[q + s * (2 * k)] = cadd(a0, a1);
-                y[q + s * (2 * k + 1)] = cmul(csub(a0, a1), W[(k * s) % N]);
+                y[q + s * (2 * k + 1)] = cmul(csub(a0, a1), W[k * s]);
             } else if (p == 4) {
                 float2 a0 = x[q + s * k], a1 = x[q + s * (k + m)], a2 = x[q + s * (k + 2 * m)], a3 = x[q + s * (k + 3 * m)];
                 float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
                 float2 t3j = make_float2(t3.y, -t3.x);                   // -j * t3
                 y[q + s * (4 * k)] = cadd(t0, t2);
-                y[q + s * (4 * k + 1)] = cmul(cadd(t1, t3j), W[(k * s) % N]);
-                y[q + s * (4 * k + 2)] = cmul(csub(t0, t2), W[(2 * k * s) % N]);
-                y[q + s * (4 * k + 3)] = cmul(csub(t1, t3j), W[(3 * k * s) % N]);
+                y[q + s * (4 * k + 1)] = cmul(cadd(t1, t3j), W[k * s]);
+                y[q + s * (4 * k + 2)] = cmul(csub(t0, t2), W[2 * k * s]);
+                y[q + s * (4 * k + 3)] = cmul(csub(t1, t3j), W[3 * k * s]);
             } else {
                 for (int c = 0; c < p; ++c) {
                     float2 acc = make_float2(0.f, 0.f);
                     for (int r = 0; r < p; ++r) acc = cadd(acc, cmul(x[q + s * (k + r * m)], W[((r * c) % p) * wstep]));
-                    y[q + s * (p * k + c)] = cmul(acc, W[(int)(((long long)c * k * s) % N)]);
+                    y[q + s * (p * k + c)] = cmul(acc, W[c * k * s]);
                 }
             }
         }
@@ -270,32 +285,41 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
 template <int WORDS>
 __global__ void gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ idx, float* __restrict__ out,
                                    long long B, int R, int J, int in_rows, int L) {
-    const long long total = B * R * (long long)J;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int j = (int)(i % J);
-        int r = (int)((i / J) % R);
-        long long b = i / ((long long)J * R);
-        int s = idx[(size_t)r * J + j];
-        const float* src = in + ((b * in_rows + (in_rows == 1 ? 0 : r)) * (long long)L + (s < 0 ? 0 : s)) * WORDS;
-        float* dst = out + i * WORDS;
-#pragma unroll
-        for (int w = 0; w < WORDS; ++w) dst[w] = s < 0 ? 0.f : src[w];
+    const long long rows = B * R;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const int r = (int)(row % R);
+        const long long b = row / R;
+        const int* ip = idx + (size_t)r * J;
+        const float* src = in + (b * in_rows + (in_rows == 1 ? 0 : r)) * (long long)L * WORDS;
+        float* dst = out + row * (long long)J * WORDS;
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            const int sidx = ip[j];
+            if (WORDS == 2) {
+                reinterpret_cast<float2*>(dst)[j] = sidx < 0 ? make_float2(0.f, 0.f) : reinterpret_cast<const float2*>(src)[sidx];
+            } else {
+                dst[j] = sidx < 0 ? 0.f : src[sidx];
+            }
+        }
     }
 }
 
 // ResourceGridMapper: map[ts, g] >= 0: data symbol index; -1: zero; <= -2: pilot index -(v + 2)
 __global__ void rg_map_kernel(const float2* __restrict__ x, const float2* __restrict__ pilots, const int* __restrict__ map,
                               float2* __restrict__ out, long long B, int TS, int G, int D, int P) {
-    const long long total = B * TS * (long long)G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int g = (int)(i % G);
-        int ts = (int)((i / G) % TS);
-        long long b = i / ((long long)G * TS);
-        int v = map[(size_t)ts * G + g];
-        float2 o = make_float2(0.f, 0.f);
-        if (v >= 0) o = x[(b * TS + ts) * (long long)D + v];
-        else if (v <= -2) o = pilots[(size_t)ts * P + (-(v + 2))];
-        out[i] = o;
+    const long long rows = B * TS;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const int ts = (int)(row % TS);
+        const int* mp = map + (size_t)ts * G;
+        const float2* xp = x + row * (long long)D;
+        const float2* pp = pilots + (size_t)ts * P;
+        float2* op = out + row * (long long)G;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const int v = mp[g];
+            float2 o = make_float2(0.f, 0.f);
+            if (v >= 0) o = xp[v];
+            else if (v <= -2) o = pp[-(v + 2)];
+            op[g] = o;
+        }
     }
 }
 
@@ -304,17 +328,21 @@ __global__ void rg_map_kernel(const float2* __restrict__ x, const float2* __rest
 __global__ void ls_at_pilots_kernel(const float2* __restrict__ y, const int* __restrict__ pilot_ind,
                                     const float2* __restrict__ pilots, const float* __restrict__ no, long long no_inner,
                                     float2* __restrict__ h, float* __restrict__ err, long long B, int TS, int P, int L) {
-    const long long total = B * TS * (long long)P;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int pp = (int)(i % ((long long)TS * P));
-        long long b = i / ((long long)TS * P);
-        float2 pl = pilots[pp];
-        float2 yy = y[b * L + pilot_ind[pp]];
-        float a2 = pl.x * pl.x + pl.y * pl.y;
-        bool z = (pl.x == 0.f && pl.y == 0.f);
-        h[i] = z ? make_float2(0.f, 0.f) : cdiv(yy, pl);
-        float ab = sqrtf(a2);                       // tf.abs(pilots)**2
-        err[i] = z ? 0.f : no[b / no_inner] / (ab * ab);
+    const long long rows = B * TS;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const int ts = (int)(row % TS);
+        const long long b = row / TS;
+        const float2* yp = y + b * (long long)L;
+        const float nb = no[b / no_inner];
+        for (int q = threadIdx.x; q < P; q += blockDim.x) {
+            const float2 pl = pilots[(size_t)ts * P + q];
+            const float2 yy = yp[pilot_ind[(size_t)ts * P + q]];
+            const float a2 = pl.x * pl.x + pl.y * pl.y;
+            const bool z = (pl.x == 0.f && pl.y == 0.f);
+            h[row * P + q] = z ? make_float2(0.f, 0.f) : cdiv(yy, pl);
+            const float ab = sqrtf(a2);                 // tf.abs(pilots)**2
+            err[row * P + q] = z ? 0.f : nb / (ab * ab);
+        }
     }
 }
 
@@ -390,22 +418,27 @@ __global__ void apply_ofdm_channel_kernel(const float2* __restrict__ x, const fl
                                           const float* __restrict__ no, long long no_inner, float2* __restrict__ y,
                                           long long B, int R, int Tt, int RE, int add_noise, unsigned long long seed,
                                           unsigned long long offset) {
-    const long long total = B * R * (long long)RE;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int re = (int)(i % RE);
-        int r = (int)((i / RE) % R);
-        long long b = i / ((long long)RE * R);
-        float2 acc = make_float2(0.f, 0.f);
-        for (int t = 0; t < Tt; ++t)
-            acc = cadd(acc, cmul(h[((b * R + r) * Tt + t) * (long long)RE + re], x[(b * Tt + t) * (long long)RE + re]));
-        if (add_noise) {
-            uint4 rr = philox4x32_10(seed, offset, (unsigned long long)i);
-            float2 g = box_muller(rr.x, rr.y);
-            float sd = sqrtf(no[i / no_inner]) * 0.70710678118654752f;
-            acc.x += g.x * sd;
-            acc.y += g.y * sd;
+    const long long rows = B * R;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const long long b = row / R;
+        const float2* hp = h + row * (long long)Tt * RE;
+        const float2* xp = x + b * (long long)Tt * RE;
+        const long long obase = row * (long long)RE;
+        const bool row_no = add_noise && (no_inner % RE) == 0;      // one noise power per row (the usual case)
+        const float sd_row = row_no ? sqrtf(no[obase / no_inner]) * 0.70710678118654752f : 0.f;
+        for (int re = threadIdx.x; re < RE; re += blockDim.x) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int t = 0; t < Tt; ++t) acc = cadd(acc, cmul(hp[(size_t)t * RE + re], xp[(size_t)t * RE + re]));
+            if (add_noise) {
+                const unsigned long long i = (unsigned long long)(obase + re);    // same Philox counter as the flat index
+                uint4 rr = philox4x32_10(seed, offset, i);
+                float2 g = box_muller(rr.x, rr.y);
+                float sd = row_no ? sd_row : sqrtf(no[i / (unsigned long long)no_inner]) * 0.70710678118654752f;
+                acc.x += g.x * sd;
+                acc.y += g.y * sd;
+            }
+            y[obase + re] = acc;
         }
-        y[i] = acc;
     }
 }
 
@@ -710,6 +743,13 @@ int make_plan(int n, FftPlan* plan) {
         if ((long long)p * p > m) p = m;             // remaining m is prime
         while (m % p == 0) { if (push(p)) return -1; m /= p; }
     }
+    int span = 1;
+    for (int st = 0; st < plan->n_radix; ++st) {
+        int lg = -1;
+        if ((span & (span - 1)) == 0) { lg = 0; while ((1 << lg) < span) ++lg; }
+        plan->span_shift[st] = lg;
+        span *= plan->radix[st];
+    }
     return 0;
 }
 
@@ -837,11 +877,11 @@ extern "C" int sb_gather_rows(const float* d_in, const int32_t* d_idx, float* d_
                  "sb_gather_rows: bad arguments");
     long long total = batch * rows * (long long)cols_out;
     if (total == 0) return SB_OK;
-    int grid = grid_for(total, 256);
+    const RowLaunch rl = row_launch(batch * rows, cols_out);
     if (words == 1)
-        gather_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
+        gather_rows_kernel<1><<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
     else
-        gather_rows_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
+        gather_rows_kernel<2><<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
@@ -852,7 +892,8 @@ extern "C" int sb_rg_map(const float* d_x, const float* d_pilots, const int32_t*
     SB_CHECK_ARG(d_x && d_map && d_out && batch >= 0 && num_streams > 0 && grid_size > 0, "sb_rg_map: bad arguments");
     long long total = batch * num_streams * (long long)grid_size;
     if (total == 0) return SB_OK;
-    rg_map_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)d_x, (const float2*)d_pilots, d_map,
+    const RowLaunch rl = row_launch(batch * num_streams, grid_size);
+    rg_map_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>((const float2*)d_x, (const float2*)d_pilots, d_map,
                                                                          (float2*)d_out, batch, num_streams, grid_size,
                                                                          num_data, num_pilots);
     SB_LAUNCH_CHECK();
@@ -867,7 +908,8 @@ extern "C" int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, con
                      num_pilots > 0 && grid_size > 0 && no_inner >= 1, "sb_ls_at_pilots: bad arguments");
     long long total = batch * num_streams * (long long)num_pilots;
     if (total == 0) return SB_OK;
-    ls_at_pilots_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const RowLaunch rl = row_launch(batch * num_streams, num_pilots);
+    ls_at_pilots_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(
         (const float2*)d_y, d_pilot_ind, (const float2*)d_pilots, d_no, no_inner, (float2*)d_h, d_err, batch, num_streams,
         num_pilots, grid_size);
     SB_LAUNCH_CHECK();
@@ -905,7 +947,8 @@ extern "C" int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const f
                      (!add_noise || (d_no && no_inner >= 1)), "sb_apply_ofdm_channel: bad arguments");
     long long total = batch * num_rx_ant_total * (long long)num_re;
     if (total == 0) return SB_OK;
-    apply_ofdm_channel_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const RowLaunch rl = row_launch(batch * num_rx_ant_total, num_re);
+    apply_ofdm_channel_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(
         (const float2*)d_x, (const float2*)d_h, d_no, no_inner > 0 ? no_inner : 1, (float2*)d_y, batch, num_rx_ant_total,
         num_tx_ant_total, num_re, add_noise, seed, offset);
     SB_LAUNCH_CHECK();
