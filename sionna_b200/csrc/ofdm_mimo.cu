@@ -190,6 +190,9 @@ struct SmallFftPlan {
     const unsigned short* tab;       // [n_stages][3][n]: in_base, twiddle index, root step
 };
 
+// FPW transforms per warp at a time: a lane owns output o of all FPW transforms, so the stage tables and the roots
+// W[widx] are loaded once per FPW complex multiply-adds. Buffers: x / y [FPW][N].
+template <int FPW>
 __device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const float2* __restrict__ W,
                                                   const unsigned short* __restrict__ tab, const SmallFftPlan& plan, int lane) {
     const int N = plan.n;
@@ -200,14 +203,21 @@ __device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const fl
         const unsigned short* t_cs = t_tw + N;
         for (int o = lane; o < N; o += 32) {
             const int in = t_in[o], cs = t_cs[o];
-            float2 acc = x[in];                                    // r = 0: root index 0 -> W = 1
+            float2 acc[FPW];
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) acc[f] = x[f * N + in];  // r = 0: root index 0 -> W = 1
             int widx = cs;
             for (int r = 1; r < p; ++r) {
-                acc = cadd(acc, cmul(x[in + r * rs], W[widx]));
+                const float2 w = W[widx];
+                const float2* xp = x + in + r * rs;
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) acc[f] = cadd(acc[f], cmul(xp[f * N], w));
                 widx += cs;
                 if (widx >= N) widx -= N;
             }
-            y[o] = cmul(acc, W[t_tw[o]]);
+            const float2 tw = W[t_tw[o]];
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) y[f * N + o] = cmul(acc[f], tw);
         }
         __syncwarp();
         float2* t = x; x = y; y = t;
@@ -215,7 +225,7 @@ __device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const fl
     return x;
 }
 
-template <int DEMOD>
+template <int DEMOD, int FPW>
 __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __restrict__ x, float2* __restrict__ out,
                                                              SmallFftPlan plan, int nsym, const int* __restrict__ cp,
                                                              const int* __restrict__ off, int len, int l_min,
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
     float2* W = sm;
     float2* PC = sm + N;                                           // phase compensation (demodulator only)
     float2* bufs = sm + (DEMOD ? 2 : 1) * N;
-    unsigned short* tab = reinterpret_cast<unsigned short*>(bufs + (size_t)2 * N * nwarps);
+    unsigned short* tab = reinterpret_cast<unsigned short*>(bufs + (size_t)2 * FPW * N * nwarps);
     for (int k = tid; k < N; k += blockDim.x) {
         float sn, cs;
         sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
@@ -237,43 +247,55 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
     }
     for (int i = tid; i < plan.n_stages * 3 * N; i += blockDim.x) tab[i] = plan.tab[i];
     __syncthreads();
-    float2* b0 = bufs + (size_t)2 * N * warp;
-    float2* b1 = b0 + N;
+    float2* b0 = bufs + (size_t)2 * FPW * N * warp;
+    float2* b1 = b0 + (size_t)FPW * N;
     const float scale = 1.0f / sqrtf((float)N);
     const long long jobs = rows * nsym;
-    for (long long job = (long long)blockIdx.x * nwarps + warp; job < jobs; job += (long long)gridDim.x * nwarps) {
-        const int l = (int)(job % nsym);
-        if (DEMOD) {
-            const float2* src = x + (job / nsym) * len + off[l] + cp[l];
-            for (int k = lane; k < N; k += 32) b0[k] = src[k];
-        } else {
-            const float2* src = x + job * N;
-            const int h = N / 2;
-            for (int k = lane; k < N; k += 32) {
-                int ks = k;
-                if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // ifftshift
-                float2 v = src[ks];
-                b0[k] = make_float2(v.x, -v.y);                    // ifft = conj(fft(conj(x))) / N
+    const int h = N / 2;
+    for (long long jb = ((long long)blockIdx.x * nwarps + warp) * FPW; jb < jobs; jb += (long long)gridDim.x * nwarps * FPW) {
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const long long job = jb + f;
+            if (job >= jobs) break;                                // tail: stale buffer contents are transformed, never stored
+            const int l = (int)(job % nsym);
+            float2* dstb = b0 + f * N;
+            if (DEMOD) {
+                const float2* src = x + (job / nsym) * len + off[l] + cp[l];
+                for (int k = lane; k < N; k += 32) dstb[k] = src[k];
+            } else {
+                const float2* src = x + job * N;
+                for (int k = lane; k < N; k += 32) {
+                    int ks = k;
+                    if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // ifftshift
+                    float2 v = src[ks];
+                    dstb[k] = make_float2(v.x, -v.y);              // ifft = conj(fft(conj(x))) / N
+                }
             }
         }
         __syncwarp();
-        const float2* res = fft_small_warp(b0, b1, W, tab, plan, lane);
-        if (DEMOD) {
-            float2* dst = out + job * N;
-            const int h = N / 2;
-            for (int k = lane; k < N; k += 32) {
-                int ks = k;
-                if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // fftshift
-                dst[ks] = cmul(cscale(res[k], scale), PC[k]);
-            }
-        } else {
-            const int c = cp[l];
-            float2* dst = out + (job / nsym) * len + off[l];
-            for (int i = lane; i < N + c; i += 32) {
-                int k = i - c;
-                if (k < 0) k += N;
-                float2 v = res[k];
-                dst[i] = make_float2(v.x * scale, -v.y * scale);
+        const float2* res = fft_small_warp<FPW>(b0, b1, W, tab, plan, lane);
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const long long job = jb + f;
+            if (job >= jobs) break;
+            const int l = (int)(job % nsym);
+            const float2* rf = res + f * N;
+            if (DEMOD) {
+                float2* dst = out + job * N;
+                for (int k = lane; k < N; k += 32) {
+                    int ks = k;
+                    if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // fftshift
+                    dst[ks] = cmul(cscale(rf[k], scale), PC[k]);
+                }
+            } else {
+                const int c = cp[l];
+                float2* dst = out + (job / nsym) * len + off[l];
+                for (int i = lane; i < N + c; i += 32) {
+                    int k = i - c;
+                    if (k < 0) k += N;
+                    float2 v = rf[k];
+                    dst[i] = make_float2(v.x * scale, -v.y * scale);
+                }
             }
         }
         __syncwarp();
@@ -796,23 +818,33 @@ int get_small_plan(int n, SmallFftPlan* out) {
 
 constexpr int kSmallFftMax = 1024;
 
+template <int DEMOD, int FPW>
+int launch_fft_small_fpw(const SmallFftPlan& sp, const float2* x, float2* out, int nsym, const int* cp, const int* off,
+                         int len, int l_min, long long rows, int shift, cudaStream_t stream) {
+    const int warps = 8, n = sp.n;
+    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * FPW * warps) +
+                  sizeof(unsigned short) * 3 * (size_t)n * sp.n_stages;
+    auto kern = ofdm_fft_small_kernel<DEMOD, FPW>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+    long long jobs = rows * nsym;
+    long long want = (jobs + (long long)warps * FPW - 1) / ((long long)warps * FPW);
+    int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sb_num_sms() * std::max(1, occ)));
+    kern<<<grid, warps * 32, smem, stream>>>(x, out, sp, nsym, cp, off, len, l_min, rows, shift);
+    return SB_OK;
+}
+
 template <int DEMOD>
 int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* cp, const int* off, int len, int l_min,
                      long long rows, int shift, cudaStream_t stream) {
     SmallFftPlan sp;
     int rc = get_small_plan(n, &sp);
     if (rc) return rc;
-    const int warps = 8;
-    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * warps) + sizeof(unsigned short) * 3 * (size_t)n * sp.n_stages;
-    auto kern = ofdm_fft_small_kernel<DEMOD>;
-    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
-    long long jobs = rows * nsym;
-    long long want = (jobs + warps - 1) / warps;
-    int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sb_num_sms() * std::max(1, occ)));
-    kern<<<grid, warps * 32, smem, stream>>>(x, out, sp, nsym, cp, off, len, l_min, rows, shift);
-    return SB_OK;
+    // transforms per warp: as many as keep two CTAs' buffers on an SM
+    if (n <= 128) return launch_fft_small_fpw<DEMOD, 4>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
+    if (n <= 384) return launch_fft_small_fpw<DEMOD, 2>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
+    return launch_fft_small_fpw<DEMOD, 1>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
 }
 }  // namespace
 
