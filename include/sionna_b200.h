@@ -131,6 +131,9 @@ int sb_ldpc5g_encode(const sb_ldpc5g_encoder* e, const float* d_u, int64_t batch
 int sb_binary_source(float* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 /* out = mean + stddev * N(0,1) (GaussianPriorSource, fec/utils.py:71-114). */
 int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint64_t seed, uint64_t offset, void* stream);
+/* config.tf_rng.uniform(shape, lo, hi) as used by TDL.__call__ (channel/tr38901/tdl.py:379-413): d_out[i] uniform in
+ * [lo, hi), Philox4x32-10 stream (seed, offset). */
+int sb_uniform(float* d_out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream);
 /* Mapper.call (mapping.py:497-519): d_bits [n_sym, m] 0/1 floats, MSB first -> d_out [n_sym] complex64 =
  * d_points[index]; d_idx_out (optional, int32 [n_sym]) receives the symbol indices (return_indices). */
 int sb_qam_map(const float* d_bits, const float* d_points, int32_t m, float* d_out, int32_t* d_idx_out,
@@ -207,6 +210,16 @@ int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, 
 int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
                           int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_re,
                           int32_t add_noise, uint64_t seed, uint64_t offset, void* stream);
+/* TDL.__call__ (channel/tr38901/tdl.py:372-456): sum-of-sinusoids tap gains. d_doppler [batch] (radian Doppler),
+ * d_theta [batch, paths, sinusoids], d_phi [batch, ant_pairs, paths, sinusoids], d_phi0 [batch] or NULL (NLoS models),
+ * d_powers [paths] -> d_a [batch, ant_pairs, paths, time_steps] complex; ant_pairs = num_rx_ant * num_tx_ant, rx major. */
+int sb_tdl_sos(const float* d_doppler, const float* d_theta, const float* d_phi, const float* d_phi0,
+               const float* d_powers, float los_power, float los_aoa, float* d_a, int64_t batch, int32_t num_ant_pairs,
+               int32_t num_paths, int32_t num_sinusoids, int32_t num_time_steps, float sampling_frequency, void* stream);
+/* cir_to_ofdm_channel (channel/utils.py:180-253) for delays shared by all links: d_a [rows, paths, time_steps] complex,
+ * d_e [paths, subcarriers] = exp(-j 2 pi f tau) -> d_h [rows, time_steps, subcarriers]. */
+int sb_cir_to_ofdm(const float* d_a, const float* d_e, float* d_h, int64_t rows, int32_t num_paths,
+                   int32_t num_time_steps, int32_t num_subcarriers, void* stream);
 /* PUSCHPrecoder.call (nr/pusch_precoder.py:75-95): d_x [batch, num_tx, num_layers, num_re] complex, d_w [num_tx,
  * num_ports, num_layers] complex -> d_y [batch, num_tx, num_ports, num_re], y = W x per resource element. */
 int sb_pusch_precode(const float* d_x, const float* d_w, float* d_y, int64_t batch, int32_t num_tx, int32_t num_layers,

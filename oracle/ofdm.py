@@ -219,3 +219,27 @@ def ofdm_lmmse_equalize(y_eff, h_hat, err_var, no, mask, sm):
     xo = np.take_along_axis(x_hat, data_ind[..., None], axis=2)
     no_o = np.take_along_axis(no_eff, data_ind[..., None], axis=2)
     return np.transpose(xo, [3, 0, 1, 2]), np.transpose(no_o, [3, 0, 1, 2])
+
+
+# ---- on-device channel generation ------------------------------------------------------------------
+def tdl_sos(doppler, theta, phi, phi0, powers, los_power, los_aoa, num_time_steps, fs):
+    """Sum-of-sinusoids tap gains (channel/tr38901/tdl.py:374-456), float64: doppler [B], theta [B, P, Ns],
+    phi [B, A, P, Ns], phi0 [B] | None, powers [P] -> a [B, A, P, T]."""
+    ns = theta.shape[-1]
+    t = np.arange(num_time_steps, dtype=np.float64) / fs                               # :374-376
+    alpha = 2 * np.pi / ns * np.arange(1, ns + 1) + theta.astype(np.float64)           # :286-288, :403
+    arg = (doppler.astype(np.float64)[:, None, None, None, None] * t[None, None, None, :, None]
+           * np.cos(alpha)[:, None, :, None, :] + phi.astype(np.float64)[:, :, :, None, :])          # :415
+    h = np.exp(1j * arg).sum(-1) / np.sqrt(ns)                                           # :417-421
+    h = np.sqrt(np.asarray(powers, np.float64))[None, None, :, None] * h                 # :423-424
+    if phi0 is not None:                                                                 # :426-448
+        spec = np.exp(1j * (doppler.astype(np.float64)[:, None] * t[None, :] * np.cos(los_aoa)
+                            + phi0.astype(np.float64)[:, None]))
+        h[:, :, 0, :] += np.sqrt(los_power) * spec[:, None, :]
+    return h
+
+
+def cir_to_ofdm(frequencies, a, tau):
+    """h[..., t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253); a [..., P, T], tau [P]."""
+    e = np.exp(-2j * np.pi * np.asarray(tau, np.float64)[:, None] * np.asarray(frequencies, np.float64)[None, :])
+    return np.einsum("...pt,pf->...tf", a, e)

@@ -987,6 +987,93 @@ extern "C" int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const f
     return SB_OK;
 }
 
+// ---- On-device channel generation (channel/tr38901/tdl.py:372-502, channel/utils.py:180-253) --------------------------
+namespace {
+// TDL tap gains by the sum-of-sinusoids model: for link b, antenna pair a (rx-major), path p, time step t
+//   a = sqrt(P_p / Ns) sum_n exp(j (w_b t/fs cos(2 pi (n+1)/Ns + theta[b,p,n]) + phi[b,a,p,n]))
+//       (+ sqrt(P_los) exp(j (w_b t/fs cos(aoa) + phi0[b])) on path 0 of the LoS models)
+// One thread per output sample; the Ns-term sum stays in registers.
+__global__ void tdl_sos_kernel(const float* __restrict__ doppler, const float* __restrict__ theta,
+                               const float* __restrict__ phi, const float* __restrict__ phi0,
+                               const float* __restrict__ powers, float los_power, float los_aoa, float2* __restrict__ out,
+                               long long B, int A, int P, int Ns, int T, float fs) {
+    const long long rows = B * A * P;                            // (b, a, p)
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const int p = (int)(row % P);
+        const long long ba = row / P;
+        const long long b = ba / A;
+        const float wd = doppler[b];
+        const float* th = theta + (b * P + p) * (long long)Ns;
+        const float* ph = phi + row * (long long)Ns;
+        const float amp = sqrtf(powers[p]) * (1.0f / sqrtf((float)Ns));
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const float ts = (float)t / fs;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int n = 0; n < Ns; ++n) {
+                const float alpha = 6.283185307179586f / (float)Ns * (float)(n + 1) + th[n];
+                float sn, cs;
+                sincosf(wd * ts * cosf(alpha) + ph[n], &sn, &cs);
+                acc.x += cs;
+                acc.y += sn;
+            }
+            float2 v = make_float2(acc.x * amp, acc.y * amp);
+            if (phi0 != nullptr && p == 0) {
+                float sn, cs;
+                sincosf(wd * ts * cosf(los_aoa) + phi0[b], &sn, &cs);
+                const float la = sqrtf(los_power);
+                v.x += la * cs;
+                v.y += la * sn;
+            }
+            out[row * T + t] = v;
+        }
+    }
+}
+
+// h[r, t, f] = sum_p a[r, p, t] e[p, f],  e[p, f] = exp(-j 2 pi f_k tau_p) shared by all links (TDL: fixed delays).
+// A CTA owns rows r = (b, rx ant, tx ant); threads walk the subcarriers: e is read coalesced, a[r, p, t] is a broadcast.
+__global__ void cir_to_ofdm_kernel(const float2* __restrict__ a, const float2* __restrict__ e, float2* __restrict__ h,
+                                   long long R, int P, int T, int F) {
+    for (long long rt = (long long)blockIdx.x * blockDim.y + threadIdx.y; rt < R * T; rt += (long long)gridDim.x * blockDim.y) {
+        const long long r = rt / T;
+        const int t = (int)(rt - r * T);
+        const float2* ap = a + r * (long long)P * T + t;
+        float2* hp = h + rt * (long long)F;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int p = 0; p < P; ++p) acc = cadd(acc, cmul(ap[(size_t)p * T], e[(size_t)p * F + f]));
+            hp[f] = acc;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int sb_tdl_sos(const float* d_doppler, const float* d_theta, const float* d_phi, const float* d_phi0,
+                          const float* d_powers, float los_power, float los_aoa, float* d_a, int64_t batch,
+                          int32_t num_ant_pairs, int32_t num_paths, int32_t num_sinusoids, int32_t num_time_steps,
+                          float sampling_frequency, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
+    SB_CHECK_ARG(d_doppler && d_theta && d_phi && d_powers && d_a && num_ant_pairs > 0 && num_paths > 0 &&
+                     num_sinusoids > 0 && num_time_steps > 0 && sampling_frequency > 0.f, "sb_tdl_sos: bad arguments");
+    const RowLaunch rl = row_launch(batch * num_ant_pairs * num_paths, num_time_steps);
+    tdl_sos_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_doppler, d_theta, d_phi, d_phi0, d_powers, los_power,
+                                                                  los_aoa, (float2*)d_a, batch, num_ant_pairs, num_paths,
+                                                                  num_sinusoids, num_time_steps, sampling_frequency);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_cir_to_ofdm(const float* d_a, const float* d_e, float* d_h, int64_t rows, int32_t num_paths,
+                              int32_t num_time_steps, int32_t num_subcarriers, void* stream) {
+    if (rows == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
+    SB_CHECK_ARG(d_a && d_e && d_h && num_paths > 0 && num_time_steps > 0 && num_subcarriers > 0,
+                 "sb_cir_to_ofdm: bad arguments");
+    const RowLaunch rl = row_launch(rows * num_time_steps, num_subcarriers);
+    cir_to_ofdm_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>((const float2*)d_a, (const float2*)d_e, (float2*)d_h,
+                                                                      rows, num_paths, num_time_steps, num_subcarriers);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
 // ---- PUSCH (nr/pusch_precoder.py, nr/pusch_channel_estimation.py) ---------------------------------------------------
 namespace {
 // y[b, t, p, re] = sum_l W[t, p, l] x[b, t, l, re]: codebook precoding of the layer grids onto the antenna ports

@@ -324,6 +324,20 @@ __global__ void normal_kernel(float* __restrict__ out, long long n, float mean, 
     }
 }
 
+// uniform variant: out = lo + (hi - lo) * u, u in [0, 1) with 24 random bits (TDL Doppler / angle / phase draws)
+__global__ void uniform_kernel(float* __restrict__ out, long long n, float lo, float hi, unsigned long long seed,
+                               unsigned long long offset) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    const float w = hi - lo;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; 4 * p < n; p += stride) {
+        uint4 r = philox4x32_10(seed, offset, (unsigned long long)p);
+        unsigned v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * p + k < n) out[4 * p + k] = lo + w * ((float)(v[k] >> 8) * 5.9604644775390625e-08f);   // 2^-24
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // counters[0] += #(b != b_hat), counters[1] += #rows with any difference, counters[2] += B*k, counters[3] += B.
 // One warp per row; block-level reduction, one atomic per block and counter.
@@ -476,6 +490,14 @@ extern "C" int sb_normal(float* d_out, int64_t n, float mean, float stddev, uint
     SB_CHECK_ARG(d_out && n >= 0, "sb_normal: bad arguments");
     if (n == 0) return SB_OK;
     normal_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(d_out, n, mean, stddev, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_uniform(float* d_out, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset, void* stream) {
+    if (n == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
+    SB_CHECK_ARG(d_out && n >= 0 && hi >= lo, "sb_uniform: bad arguments");
+    uniform_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(d_out, n, lo, hi, seed, offset);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

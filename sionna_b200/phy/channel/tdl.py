@@ -1,15 +1,15 @@
-"""Block-fading TDL channel models and CIR -> OFDM channel conversion ("next tier" input generation of SURVEY.md
-section 8(f3); mirror of /root/reference/src/sionna/phy/channel/tr38901/tdl.py:372-502 for zero speed and of
-channel/utils.py:180-253, 1010-1060). Power delay profiles: TR 38.901 Tables 7.7.2-1..5 (``tdl_models.npz``).
-The tap gains are drawn on the device (``complex_normal`` -> ``sb_awgn``'s Philox generator); the frequency response is
-assembled with a few torch tensor ops (input generation, not part of the graded receive path)."""
+"""TDL channel models (sum-of-sinusoids time evolution) and CIR -> OFDM channel conversion: on-device channel generation
+of SURVEY.md section 8(f3); mirror of /root/reference/src/sionna/phy/channel/tr38901/tdl.py:20-590 and of
+channel/utils.py:180-253, 1010-1060. Power delay profiles: TR 38.901 Tables 7.7.2-1..5 and TS 38.104 Annex G
+(``tdl_models.npz``, tools/make_code_tables.py). Random draws (``sb_uniform``), tap synthesis (``sb_tdl_sos``) and the
+frequency response (``sb_cir_to_ofdm``) are hand-written kernels."""
 import os
 import numpy as np
 import torch
 
 from ..block import Block
 from ..config import config
-from ..utils.misc import complex_normal
+from ..._lib import lib, check, ptr, current_stream
 
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tdl_models.npz")
 
@@ -23,15 +23,37 @@ def subcarrier_frequencies(num_subcarriers, subcarrier_spacing, precision=None):
     return torch.arange(start, limit, dtype=torch.float32) * subcarrier_spacing
 
 
+def _uniform(shape, lo, hi):
+    """config.tf_rng.uniform(shape, lo, hi) on the device (``sb_uniform``, Philox4x32-10)."""
+    out = torch.empty([int(v) for v in shape], dtype=torch.float32, device=config.device)
+    seed, off = config.next_philox()
+    check(lib().sb_uniform(ptr(out), out.numel(), float(lo), float(hi), seed, off, current_stream()), "sb_uniform")
+    return out
+
+
 def cir_to_ofdm_channel(frequencies, a, tau, normalize=False):
-    """h_f[b, rx, rx_ant, tx, tx_ant, t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253)."""
+    """h_f[b, rx, rx_ant, tx, tx_ant, t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253).
+
+    Delays shared by every link (all TDL models; detected on the tensor): one kernel, ``sb_cir_to_ofdm``, with the
+    [paths, subcarriers] phase table built once. Per-link delays fall back to a batched tensor contraction."""
     dev = a.device
-    f = frequencies.to(dev)
+    f = frequencies.to(device=dev, dtype=torch.float32)
     tau = tau.to(dev)
-    if tau.dim() == 4:                                        # [b, rx, tx, paths] -> broadcast over antennas
-        tau = tau[:, :, None, :, None, :]
-    e = torch.exp(torch.complex(torch.zeros((), device=dev), -2 * np.pi * tau[..., None] * f))   # [..., paths, F]
-    h = torch.einsum("brmtnpl,brmtnpf->brmtnlf", a, e.expand(*a.shape[:-1], f.shape[0]).to(a.dtype))
+    shared = tau.numel() > 0 and bool((tau == tau.reshape(-1, tau.shape[-1])[0]).all())
+    if shared and a.dtype == torch.complex64 and a.dim() == 7:
+        b, rx, ra, tx, ta, p, t = a.shape
+        t0 = tau.reshape(-1, tau.shape[-1])[0].to(torch.float32)                       # [paths]
+        ang = -2 * np.pi * t0[:, None].double() * f[None, :].double()
+        e = torch.complex(torch.cos(ang), torch.sin(ang)).to(torch.complex64).contiguous()
+        ac = a.contiguous()
+        h = torch.empty((b, rx, ra, tx, ta, t, f.shape[0]), dtype=torch.complex64, device=dev)
+        check(lib().sb_cir_to_ofdm(ptr(ac), ptr(e), ptr(h), b * rx * ra * tx * ta, p, t, f.shape[0], current_stream()),
+              "sb_cir_to_ofdm")
+    else:
+        if tau.dim() == 4:                                    # [b, rx, tx, paths] -> broadcast over antennas
+            tau = tau[:, :, None, :, None, :]
+        e = torch.exp(torch.complex(torch.zeros((), device=dev), -2 * np.pi * tau[..., None] * f))   # [..., paths, F]
+        h = torch.einsum("brmtnpl,brmtnpf->brmtnlf", a, e.expand(*a.shape[:-1], f.shape[0]).to(a.dtype))
     if normalize:
         c = torch.sqrt(torch.mean(torch.abs(h) ** 2, dim=(2, 4, 5, 6), keepdim=True))
         h = h / c.to(h.dtype)
@@ -39,56 +61,143 @@ def cir_to_ofdm_channel(frequencies, a, tau, normalize=False):
 
 
 class TDL(Block):
-    """TDL(model, delay_spread, carrier_frequency, num_rx_ant=1, num_tx_ant=1, min_speed=0., max_speed=None)
+    """TDL(model, delay_spread, carrier_frequency, num_sinusoids=20, los_angle_of_arrival=pi/4, min_speed=0., max_speed=None, num_rx_ant=1, num_tx_ant=1, spatial_corr_mat=None, rx_corr_mat=None, tx_corr_mat=None, precision=None)
 
-    Tapped delay line model "A".."E" of TR 38.901 with RMS delay spread ``delay_spread`` [s]; block fading (zero
-    speed): ``call(batch_size, num_time_steps, sampling_frequency)`` -> ``a [batch, 1, num_rx_ant, 1, num_tx_ant,
-    num_paths, num_time_steps]`` (constant over time), ``tau [batch, 1, 1, num_paths]``. Average total power is 1."""
+    Tapped delay line models "A".."E" of TR 38.901 (delays scaled by ``delay_spread`` [s]) and "A30", "B100", "C300" of
+    TS 38.104 (fixed delays). Time evolution by the sum-of-sinusoids model of the reference (tdl.py:372-456): a Doppler
+    shift per link drawn in [w(min_speed), w(max_speed)], w = 2 pi v f_c / c, ``num_sinusoids`` arrival angles per path
+    and a phase per antenna pair, path and sinusoid; LoS models add a specular term on the first path.
 
-    def __init__(self, model, delay_spread, carrier_frequency, num_rx_ant=1, num_tx_ant=1, min_speed=0., max_speed=None,
-                 precision=None, **kwargs):
+    ``call(batch_size, num_time_steps, sampling_frequency)`` -> ``a [batch, 1, num_rx_ant, 1, num_tx_ant, num_paths,
+    num_time_steps]`` complex64, ``tau [batch, 1, 1, num_paths]``. All draws and the tap synthesis run on the device
+    (``sb_uniform``, ``sb_tdl_sos``)."""
+
+    def __init__(self, model, delay_spread, carrier_frequency, num_sinusoids=20, los_angle_of_arrival=np.pi / 4,
+                 min_speed=0., max_speed=None, num_rx_ant=1, num_tx_ant=1, spatial_corr_mat=None, rx_corr_mat=None,
+                 tx_corr_mat=None, precision=None, **kwargs):
         super().__init__(precision=precision, **kwargs)
-        assert model in ("A", "B", "C", "D", "E"), "Invalid TDL model"
-        if (min_speed or 0.) != 0. or (max_speed or 0.) != 0.:
-            raise NotImplementedError("TDL: only block fading (zero speed) is provided.")
+        assert model in ("A", "B", "C", "D", "E", "A30", "B100", "C300"), "Invalid TDL model"
+        fixed = {"A30": 30e-9, "B100": 100e-9, "C300": 300e-9}
+        if model in fixed and delay_spread != fixed[model]:
+            print(f"Warning: Delay spread is set to {fixed[model] * 1e9:.0f}ns with this model")
+            delay_spread = fixed[model]
         with np.load(_MODELS) as d:
             delays, p_db, los = d[f"{model}_delays"], d[f"{model}_powers_db"], int(d[f"{model}_los"])
+            self._scale_delays = bool(int(d[f"{model}_scale_delays"]))
         p = 10 ** (p_db / 10)
         self._los = bool(los)
-        if self._los:                                          # first entry = LoS component sharing the first delay
-            self._los_power = p[0]
+        self._los_power = 0.0
+        if self._los:                                          # first entry = specular component sharing the first delay
+            self._los_power = float(p[0])
             p, delays = p[1:], delays[1:]
-            norm = self._los_power + p.sum()
-            self._los_power /= norm
-            p = p / norm
-        else:
-            p = p / p.sum()
-        self._powers = p.astype(np.float32)
-        self._delays = (delays * delay_spread).astype(np.float32)
-        self._num_rx_ant, self._num_tx_ant = num_rx_ant, num_tx_ant
+        norm = self._los_power + p.sum()                       # total mean power 1 (tdl.py:583-590)
+        self._los_power /= norm
+        self._powers = (p / norm).astype(np.float32)
+        self._delays_norm = delays.astype(np.float64)
+        self._delay_spread = float(delay_spread)
+        self._num_rx_ant, self._num_tx_ant = int(num_rx_ant), int(num_tx_ant)
+        self._carrier_frequency = float(carrier_frequency)
+        self._num_sinusoids = int(num_sinusoids)
+        self._los_aoa = float(los_angle_of_arrival)
+        self._min_speed = float(min_speed)
+        self._max_speed = self._min_speed if max_speed is None else float(max_speed)
+        assert self._max_speed >= self._min_speed, "min_speed cannot be larger than max_speed"
+        self._corr = None
+        if spatial_corr_mat is not None:
+            m = torch.as_tensor(np.asarray(spatial_corr_mat), dtype=torch.complex64)
+            self._corr = ("full", torch.linalg.cholesky(m))
+        elif rx_corr_mat is not None or tx_corr_mat is not None:
+            r = None if rx_corr_mat is None else torch.linalg.cholesky(torch.as_tensor(np.asarray(rx_corr_mat), dtype=torch.complex64))
+            t = None if tx_corr_mat is None else torch.linalg.cholesky(torch.as_tensor(np.asarray(tx_corr_mat), dtype=torch.complex64))
+            self._corr = ("kron", r, t)
+        self._dev_powers = None
+
+    def _doppler(self, speed):
+        """Maximum radian Doppler 2 pi v f_c / c (tdl.py:504-527)."""
+        return 2.0 * np.pi * speed / 299792458.0 * self._carrier_frequency
+
+    num_clusters = property(lambda self: len(self._powers))
+    los = property(lambda self: self._los)
 
     @property
-    def num_clusters(self):
-        return len(self._powers)
+    def k_factor(self):
+        assert self._los, "This property is only available for LoS models"
+        return self._los_power / float(self._powers[0])
 
     @property
     def delays(self):
-        return torch.from_numpy(self._delays)
+        scale = self._delay_spread if self._scale_delays else 1e-9
+        return torch.from_numpy((self._delays_norm * scale).astype(np.float32))
 
     @property
     def mean_powers(self):
-        return torch.from_numpy(self._powers)
+        p = self._powers.copy()
+        if self._los:
+            p[0] += self._los_power
+        return torch.from_numpy(p)
+
+    @property
+    def mean_power_los(self):
+        assert self._los, "This property is only available for LoS models"
+        return self._los_power
+
+    @property
+    def delay_spread(self):
+        return self._delay_spread
+
+    @delay_spread.setter
+    def delay_spread(self, value):
+        if self._scale_delays:
+            self._delay_spread = float(value)
+        else:
+            print("Warning: The delay spread cannot be set with this model")
 
     def __call__(self, batch_size, num_time_steps=1, sampling_frequency=1.0):
         return self.call(batch_size, num_time_steps, sampling_frequency)
 
+    def draws(self, batch_size):
+        """The random draws of one call: (doppler [B], theta [B, P, Ns], phi [B, A, P, Ns], phi0 [B] | None)."""
+        n, ns, ap = self.num_clusters, self._num_sinusoids, self._num_rx_ant * self._num_tx_ant
+        doppler = _uniform([batch_size], self._doppler(self._min_speed), self._doppler(self._max_speed))
+        theta = _uniform([batch_size, n, ns], -np.pi / ns, np.pi / ns)
+        phi = _uniform([batch_size, ap, n, ns], -np.pi, np.pi)
+        phi0 = _uniform([batch_size], -np.pi, np.pi) if self._los else None
+        return doppler, theta, phi, phi0
+
+    def synthesize(self, draws, num_time_steps, sampling_frequency):
+        """Tap gains [B, num_rx_ant * num_tx_ant, P, T] from `draws` (kernel ``sb_tdl_sos``)."""
+        doppler, theta, phi, phi0 = draws
+        dev = doppler.device
+        b, n, ns = doppler.shape[0], self.num_clusters, self._num_sinusoids
+        ap = self._num_rx_ant * self._num_tx_ant
+        if self._dev_powers is None or self._dev_powers.device != dev:
+            self._dev_powers = torch.from_numpy(self._powers).to(dev)
+        a = torch.empty((b, ap, n, int(num_time_steps)), dtype=torch.complex64, device=dev)
+        check(lib().sb_tdl_sos(ptr(doppler), ptr(theta), ptr(phi), ptr(phi0), ptr(self._dev_powers), self._los_power,
+                               self._los_aoa, ptr(a), b, ap, n, ns, int(num_time_steps), float(sampling_frequency),
+                               current_stream()), "sb_tdl_sos")
+        return a
+
     def call(self, batch_size, num_time_steps=1, sampling_frequency=1.0):
-        dev = config.device
-        n = self.num_clusters
-        g = complex_normal([batch_size, 1, self._num_rx_ant, 1, self._num_tx_ant, n, 1])
-        a = g * torch.sqrt(torch.from_numpy(self._powers).to(dev)).reshape(1, 1, 1, 1, 1, n, 1)
-        if self._los:
-            a[..., 0, :] = a[..., 0, :] + np.sqrt(self._los_power)
-        a = a.expand(batch_size, 1, self._num_rx_ant, 1, self._num_tx_ant, n, num_time_steps).contiguous()
-        tau = torch.from_numpy(self._delays).to(dev).reshape(1, 1, 1, n).expand(batch_size, 1, 1, n).contiguous()
+        if self.precision != "single":
+            raise NotImplementedError("TDL generates complex64 taps only.")
+        batch_size = int(batch_size)
+        a = self.synthesize(self.draws(batch_size), num_time_steps, sampling_frequency)
+        n, t = self.num_clusters, int(num_time_steps)
+        a = a.reshape(batch_size, 1, self._num_rx_ant, 1, self._num_tx_ant, n, t)
+        if self._corr is not None:                              # spatial correlation: small dense factors (tdl.py:466-490)
+            if self._corr[0] == "full":
+                l = self._corr[1].to(a.device)
+                v = a.permute(0, 1, 3, 5, 6, 2, 4).reshape(batch_size, 1, 1, n, t, -1)
+                v = torch.einsum("ij,...j->...i", l, v).reshape(batch_size, 1, 1, n, t, self._num_rx_ant, self._num_tx_ant)
+                a = v.permute(0, 1, 5, 2, 6, 3, 4).contiguous()
+            else:
+                _, r, tt = self._corr
+                v = a.permute(0, 1, 3, 5, 6, 2, 4)                 # [..., rx_ant, tx_ant]
+                if r is not None:
+                    v = torch.matmul(r.to(a.device), v)
+                if tt is not None:
+                    v = torch.matmul(v, tt.to(a.device).conj().transpose(-1, -2))
+                a = v.permute(0, 1, 5, 2, 6, 3, 4).contiguous()
+        tau = self.delays.to(a.device).reshape(1, 1, 1, n).expand(batch_size, 1, 1, n).contiguous()
         return a, tau

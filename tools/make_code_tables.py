@@ -34,11 +34,12 @@ for i, p in enumerate(pcms): print("pcm", i, np.array(p).shape)
 import json
 tdl = {}
 mdir = "/root/reference/src/sionna/phy/channel/tr38901/models"
-for m in "ABCDE":
+for m in ("A", "B", "C", "D", "E", "A30", "B100", "C300"):   # the last three: TS 38.104 Annex G, delays in ns
     with open(os.path.join(mdir, f"TDL-{m}.json")) as f:
         d = json.load(f)
     tdl[f"{m}_delays"] = np.array(d["delays"], np.float64)
     tdl[f"{m}_powers_db"] = np.array(d["powers"], np.float64)
     tdl[f"{m}_los"] = np.array(int(d["los"]))
+    tdl[f"{m}_scale_delays"] = np.array(int(d["scale_delays"]))
     print("TDL-" + m, d["num_clusters"], "taps, los", d["los"])
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "..", "sionna_b200", "phy", "channel", "tdl_models.npz"), **tdl)
