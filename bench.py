@@ -305,10 +305,10 @@ def main():
                                               "kernel_ms": ms,
                                               "roofline_frac": ALG_BYTES_PER_CW * BATCH / (ms * 1e-3) / 1e9 / peak,
                                               "traffic": measured_traffic("minsum")}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:           # reported baseline: rank 0 at N = 1 only
             from oracle import ldpc as O
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample or max(2 * cores, 64)
+            sample = min(BATCH, args.cpu_sample or max(32 * cores, 1024))   # ~10 s of CPU work on 128 threads
             ref = O.LDPC5GDecoderRef(O.LDPC5GEncoderRef(K_INFO, N_CODE), cn_update=args.cn_update, num_iter=NUM_ITER)
             x = h_in[0][:sample].numpy()
             ref(x[:cores], num_threads=cores)
