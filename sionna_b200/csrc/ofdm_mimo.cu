@@ -992,39 +992,52 @@ namespace {
 // TDL tap gains by the sum-of-sinusoids model: for link b, antenna pair a (rx-major), path p, time step t
 //   a = sqrt(P_p / Ns) sum_n exp(j (w_b t/fs cos(2 pi (n+1)/Ns + theta[b,p,n]) + phi[b,a,p,n]))
 //       (+ sqrt(P_los) exp(j (w_b t/fs cos(aoa) + phi0[b])) on path 0 of the LoS models)
-// One thread per output sample; the Ns-term sum stays in registers.
+// One thread per (b, a, p) row. Time is processed in chunks of 16 steps held in registers: per sinusoid one cos for the
+// angular rate, one sincos for the phasor at the chunk start and one for the per-step rotation, then 16 complex
+// multiplications (the recurrence is re-anchored every chunk, so its rounding error stays below 1e-6).
+constexpr int kSosChunk = 16;
+__device__ __forceinline__ void sos_accumulate(float2* acc, float rate, float phase, int t0) {
+    float s0, c0, sd, cd;
+    sincosf(rate * (float)t0 + phase, &s0, &c0);
+    sincosf(rate, &sd, &cd);
+    float2 z = make_float2(c0, s0);
+    const float2 step = make_float2(cd, sd);
+#pragma unroll
+    for (int i = 0; i < kSosChunk; ++i) {
+        acc[i].x += z.x;
+        acc[i].y += z.y;
+        z = cmul(z, step);
+    }
+}
 __global__ void tdl_sos_kernel(const float* __restrict__ doppler, const float* __restrict__ theta,
                                const float* __restrict__ phi, const float* __restrict__ phi0,
                                const float* __restrict__ powers, float los_power, float los_aoa, float2* __restrict__ out,
                                long long B, int A, int P, int Ns, int T, float fs) {
     const long long rows = B * A * P;                            // (b, a, p)
-    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(row % P);
-        const long long ba = row / P;
-        const long long b = ba / A;
-        const float wd = doppler[b];
+        const long long b = row / ((long long)P * A);
+        const float wd = doppler[b] / fs;                        // radians per time step at cos = 1
         const float* th = theta + (b * P + p) * (long long)Ns;
         const float* ph = phi + row * (long long)Ns;
         const float amp = sqrtf(powers[p]) * (1.0f / sqrtf((float)Ns));
-        for (int t = threadIdx.x; t < T; t += blockDim.x) {
-            const float ts = (float)t / fs;
-            float2 acc = make_float2(0.f, 0.f);
+        const bool los = phi0 != nullptr && p == 0;
+        const float la = los ? sqrtf(los_power) : 0.f;
+        for (int t0 = 0; t0 < T; t0 += kSosChunk) {
+            float2 acc[kSosChunk];
+#pragma unroll
+            for (int i = 0; i < kSosChunk; ++i) acc[i] = make_float2(0.f, 0.f);
             for (int n = 0; n < Ns; ++n) {
                 const float alpha = 6.283185307179586f / (float)Ns * (float)(n + 1) + th[n];
-                float sn, cs;
-                sincosf(wd * ts * cosf(alpha) + ph[n], &sn, &cs);
-                acc.x += cs;
-                acc.y += sn;
+                sos_accumulate(acc, wd * cosf(alpha), ph[n], t0);
             }
-            float2 v = make_float2(acc.x * amp, acc.y * amp);
-            if (phi0 != nullptr && p == 0) {
-                float sn, cs;
-                sincosf(wd * ts * cosf(los_aoa) + phi0[b], &sn, &cs);
-                const float la = sqrtf(los_power);
-                v.x += la * cs;
-                v.y += la * sn;
-            }
-            out[row * T + t] = v;
+            float2 spec[kSosChunk];
+#pragma unroll
+            for (int i = 0; i < kSosChunk; ++i) spec[i] = make_float2(0.f, 0.f);
+            if (los) sos_accumulate(spec, wd * cosf(los_aoa), phi0[b], t0);
+#pragma unroll
+            for (int i = 0; i < kSosChunk; ++i)
+                if (t0 + i < T) out[row * T + t0 + i] = make_float2(acc[i].x * amp + la * spec[i].x, acc[i].y * amp + la * spec[i].y);
         }
     }
 }
@@ -1054,8 +1067,7 @@ extern "C" int sb_tdl_sos(const float* d_doppler, const float* d_theta, const fl
     if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_doppler && d_theta && d_phi && d_powers && d_a && num_ant_pairs > 0 && num_paths > 0 &&
                      num_sinusoids > 0 && num_time_steps > 0 && sampling_frequency > 0.f, "sb_tdl_sos: bad arguments");
-    const RowLaunch rl = row_launch(batch * num_ant_pairs * num_paths, num_time_steps);
-    tdl_sos_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_doppler, d_theta, d_phi, d_phi0, d_powers, los_power,
+    tdl_sos_kernel<<<grid_for(batch * num_ant_pairs * num_paths, 128), 128, 0, (cudaStream_t)stream>>>(d_doppler, d_theta, d_phi, d_phi0, d_powers, los_power,
                                                                   los_aoa, (float2*)d_a, batch, num_ant_pairs, num_paths,
                                                                   num_sinusoids, num_time_steps, sampling_frequency);
     SB_LAUNCH_CHECK();

@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(128) demap_kernel(const float2* __restrict__ y
                 }
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
-                    float a1 = __fadd_rn(sm1[i] > 0.f ? sb_logf(sm1[i]) : -INFINITY, mx1[i]);
-                    float a0 = __fadd_rn(sm0[i] > 0.f ? sb_logf(sm0[i]) : -INFINITY, mx0[i]);
+                    const float2 lg = sb_logf2(make_float2(fmaxf(sm0[i], 1.17549435e-38f), fmaxf(sm1[i], 1.17549435e-38f)));
+                    float a1 = __fadd_rn(sm1[i] > 0.f ? lg.y : -INFINITY, mx1[i]);
+                    float a0 = __fadd_rn(sm0[i] > 0.f ? lg.x : -INFINITY, mx0[i]);
                     out[i] = __fsub_rn(a1, a0);
                 }
             }
@@ -243,8 +244,10 @@ __global__ void __launch_bounds__(128) demap_qam_kernel(const float2* __restrict
                             s0 = __fadd_rn(s0, r.x);
                             s1 = __fadd_rn(s1, r.y);
                         }
-                        float b1 = __fadd_rn(s1 > 0.f ? sb_logf(s1) : -INFINITY, mx1);
-                        float b0 = __fadd_rn(s0 > 0.f ? sb_logf(s0) : -INFINITY, mx0);
+                        // both logs in one packed evaluation (sb_logf2 is bit-identical to sb_logf per element)
+                        const float2 lg = sb_logf2(make_float2(fmaxf(s0, 1.17549435e-38f), fmaxf(s1, 1.17549435e-38f)));
+                        float b1 = __fadd_rn(s1 > 0.f ? lg.y : -INFINITY, mx1);
+                        float b0 = __fadd_rn(s0 > 0.f ? lg.x : -INFINITY, mx0);
                         l = __fsub_rn(b1, b0);
                     }
                     out[2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
