@@ -122,10 +122,29 @@ def run_reference(args):
                              "sample": f"{sample} codewords/step x {args.steps} steps, oracle/ldpc_bp_ref.c libm mode, "
                                        f"OpenMP {cores} threads (TensorFlow reference not installable offline)"},
             "e2e": {"value": val, "unit": "coded bits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """Writes the ONE result line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that might write to fd 1 (NCCL's version banner, library
+    # printf, build logs) is routed to stderr for the lifetime of the process
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -321,7 +340,7 @@ def main():
                                     "sample": f"first {sample} codewords of the step-0 batch, oracle/ldpc_bp_ref.c libm "
                                               f"mode, {cores} OpenMP threads",
                                     "bit_mismatch_vs_gpu": int((u_ref != u_gpu).sum())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
