@@ -210,6 +210,12 @@ int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, 
 int sb_apply_ofdm_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
                           int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_re,
                           int32_t add_noise, uint64_t seed, uint64_t offset, void* stream);
+/* ApplyTimeChannel.call (channel/apply_time_channel.py:115-137): d_x [batch, num_tx_ant_total, num_time_samples], d_h
+ * [batch, num_rx_ant_total, num_tx_ant_total, num_time_samples + l_tot - 1, l_tot] -> d_y [batch, num_rx_ant_total,
+ * num_time_samples + l_tot - 1] = time-variant FIR of x (+ CN(0, no) noise if add_noise). */
+int sb_apply_time_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
+                          int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total, int32_t num_time_samples,
+                          int32_t l_tot, int32_t add_noise, uint64_t seed, uint64_t offset, void* stream);
 /* TDL.__call__ (channel/tr38901/tdl.py:372-456): sum-of-sinusoids tap gains. d_doppler [batch] (radian Doppler),
  * d_theta [batch, paths, sinusoids], d_phi [batch, ant_pairs, paths, sinusoids], d_phi0 [batch] or NULL (NLoS models),
  * d_powers [paths] -> d_a [batch, ant_pairs, paths, time_steps] complex; ant_pairs = num_rx_ant * num_tx_ant, rx major. */

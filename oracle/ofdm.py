@@ -243,3 +243,24 @@ def cir_to_ofdm(frequencies, a, tau):
     """h[..., t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253); a [..., P, T], tau [P]."""
     e = np.exp(-2j * np.pi * np.asarray(tau, np.float64)[:, None] * np.asarray(frequencies, np.float64)[None, :])
     return np.einsum("...pt,pf->...tf", a, e)
+
+
+def cir_to_time(bandwidth, a, tau, l_min, l_max):
+    """hm[..., t, l] = sum_p a[..., p, t] sinc(l - tau_p W) (channel/utils.py:320-336); a [..., P, T], tau [P]."""
+    l = np.arange(l_min, l_max + 1, dtype=np.float64)
+    g = np.sinc(l[None, :] - np.asarray(tau, np.float64)[:, None] * bandwidth)           # [P, L]
+    return np.einsum("...pt,pl->...tl", a, g)
+
+
+def apply_time_channel(x, h):
+    """y[b, r, n] = sum_t sum_l h[b, r, t, n, l] x[b, t, n - l], x zero outside [0, N) (apply_time_channel.py:115-133).
+    x [B, Tt, N], h [B, R, Tt, N + L - 1, L] -> [B, R, N + L - 1]."""
+    b, r, tt, no, l_tot = h.shape
+    n = x.shape[-1]
+    xp = np.concatenate([x, np.zeros(x.shape[:-1] + (l_tot,), x.dtype)], -1)
+    y = np.zeros((b, r, no), complex)
+    for nn in range(no):
+        for l in range(l_tot):
+            if 0 <= nn - l < n:
+                y[:, :, nn] += np.einsum("brt,bt->br", h[:, :, :, nn, l], xp[:, :, nn - l])
+    return y

@@ -48,6 +48,7 @@ SIGNATURES = {
     "sb_ls_at_pilots": (i32, [vp, vp, vp, vp, i64, vp, vp, i64, i32, i32, i32, vp]),
     "sb_interp_lin": (i32, [vp] * 8 + [i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "sb_apply_ofdm_channel": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, u64, u64, vp]),
+    "sb_apply_time_channel": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, u64, u64, vp]),
     "sb_uniform": (i32, [vp, i64, f32, f32, u64, u64, vp]),
     "sb_tdl_sos": (i32, [vp, vp, vp, vp, vp, f32, f32, vp, i64, i32, i32, i32, i32, f32, vp]),
     "sb_cir_to_ofdm": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),

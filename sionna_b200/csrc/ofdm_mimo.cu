@@ -1060,6 +1060,57 @@ __global__ void cir_to_ofdm_kernel(const float2* __restrict__ a, const float2* _
 }
 }  // namespace
 
+namespace {
+// ApplyTimeChannel (channel/apply_time_channel.py:115-137): time-variant FIR filtering
+//   y[b, r, n] = sum_t sum_l h[b, r, t, n, l] x[b, t, n - l]   (x = 0 outside [0, N)),  n in [0, N + L - 1)
+// r = (rx, rx_ant), t = (tx, tx_ant). A CTA row is (b, r); threads walk the output samples.
+__global__ void apply_time_channel_kernel(const float2* __restrict__ x, const float2* __restrict__ h,
+                                          const float* __restrict__ no, long long no_inner, float2* __restrict__ y,
+                                          long long B, int R, int Tt, int N, int L, int add_noise, unsigned long long seed,
+                                          unsigned long long offset) {
+    const int NO = N + L - 1;
+    const long long rows = B * R;
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const long long b = row / R;
+        const long long obase = row * (long long)NO;
+        for (int n = threadIdx.x; n < NO; n += blockDim.x) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int t = 0; t < Tt; ++t) {
+                const float2* hp = h + ((row * Tt + t) * (long long)NO + n) * L;
+                const float2* xp = x + (b * Tt + t) * (long long)N;
+                const int l0 = n - (N - 1) > 0 ? n - (N - 1) : 0;     // n - l <= N - 1
+                const int l1 = n < L - 1 ? n : L - 1;                  // n - l >= 0
+                for (int l = l0; l <= l1; ++l) acc = cadd(acc, cmul(hp[l], xp[n - l]));
+            }
+            if (add_noise) {
+                const unsigned long long i = (unsigned long long)(obase + n);
+                uint4 rr = philox4x32_10(seed, offset, i);
+                float2 g = box_muller(rr.x, rr.y);
+                float sd = sqrtf(no[i / (unsigned long long)no_inner]) * 0.70710678118654752f;
+                acc.x += g.x * sd;
+                acc.y += g.y * sd;
+            }
+            y[obase + n] = acc;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int sb_apply_time_channel(const float* d_x, const float* d_h, const float* d_no, int64_t no_inner, float* d_y,
+                                     int64_t batch, int32_t num_rx_ant_total, int32_t num_tx_ant_total,
+                                     int32_t num_time_samples, int32_t l_tot, int32_t add_noise, uint64_t seed,
+                                     uint64_t offset, void* stream) {
+    if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
+    SB_CHECK_ARG(d_x && d_h && d_y && num_rx_ant_total > 0 && num_tx_ant_total > 0 && num_time_samples > 0 && l_tot > 0 &&
+                     (!add_noise || (d_no && no_inner >= 1)), "sb_apply_time_channel: bad arguments");
+    const RowLaunch rl = row_launch(batch * num_rx_ant_total, num_time_samples + l_tot - 1);
+    apply_time_channel_kernel<<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(
+        (const float2*)d_x, (const float2*)d_h, d_no, no_inner > 0 ? no_inner : 1, (float2*)d_y, batch, num_rx_ant_total,
+        num_tx_ant_total, num_time_samples, l_tot, add_noise, seed, offset);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
 extern "C" int sb_tdl_sos(const float* d_doppler, const float* d_theta, const float* d_phi, const float* d_phi0,
                           const float* d_powers, float los_power, float los_aoa, float* d_a, int64_t batch,
                           int32_t num_ant_pairs, int32_t num_paths, int32_t num_sinusoids, int32_t num_time_steps,

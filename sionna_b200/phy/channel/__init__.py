@@ -1,4 +1,6 @@
-"""Channel models on the hot path (mirror of sionna.phy.channel): AWGN, frequency-domain channel application."""
+"""Channel models and channel application (mirror of sionna.phy.channel, SURVEY.md section 8 rows a / f3)."""
 from .awgn import AWGN
 from .apply_ofdm_channel import ApplyOFDMChannel
 from .tdl import TDL, cir_to_ofdm_channel, subcarrier_frequencies
+from .time_channel import (time_lag_discrete_time_channel, cir_to_time_channel, ApplyTimeChannel, GenerateOFDMChannel,
+                           OFDMChannel, GenerateTimeChannel, TimeChannel)

@@ -91,3 +91,67 @@ def test_pusch_link_with_mobility(cuda_device):
     y = ApplyOFDMChannel()(x, h, 0.01)
     b_hat, crc = rx(y, 0.01)
     assert float((b_hat != b).float().mean()) < 1e-3 and float(crc.float().mean()) > 0.99
+
+
+def test_time_channel_vs_oracle_and_ofdm_equivalence(cuda_device):
+    """cir_to_time_channel / ApplyTimeChannel equal their NumPy restatements, and for a static channel the time-domain
+    path (OFDM modulator -> time-variant filter -> OFDM demodulator) reproduces the frequency-domain channel application
+    up to the sinc truncation (the reference's time/frequency equivalence check)."""
+    from sionna_b200.phy.channel import (TDL, cir_to_time_channel, cir_to_ofdm_channel, ApplyTimeChannel, ApplyOFDMChannel,
+                                         subcarrier_frequencies, time_lag_discrete_time_channel, TimeChannel, OFDMChannel)
+    from sionna_b200.phy.ofdm import OFDMModulator, OFDMDemodulator, ResourceGrid
+    from sionna_b200.phy.utils import complex_normal
+    from sionna_b200.phy import config
+    from oracle import ofdm as OO
+    config.seed = 9
+    fft, cp, nsym, scs = 64, 16, 4, 30e3
+    bw = fft * scs
+    l_min, l_max = time_lag_discrete_time_channel(bw, 300e-9)
+    assert l_min == -6 and l_max == int(np.ceil(300e-9 * bw)) + 6
+    l_tot = l_max - l_min + 1
+    n_time = nsym * (fft + cp)
+    tdl = TDL("A", 50e-9, 3.5e9, num_rx_ant=2, num_tx_ant=2)
+    a, tau = tdl(6, n_time + l_tot - 1, bw)                                  # zero speed: constant taps
+    hm = cir_to_time_channel(bw, a, tau, l_min, l_max)
+    ref = OO.cir_to_time(bw, a.cpu().numpy().astype(np.complex128), tdl.delays.numpy(), l_min, l_max)
+    assert list(hm.shape) == [6, 1, 2, 1, 2, n_time + l_tot - 1, l_tot]
+    assert np.allclose(hm.cpu().numpy(), ref, atol=2e-5)
+    x = complex_normal([6, 1, 2, nsym, fft])
+    xt = OFDMModulator(cp)(x)                                                # [6, 1, 2, n_time]
+    yt = ApplyTimeChannel(n_time, l_tot)(xt, hm)
+    yt_ref = OO.apply_time_channel(xt.cpu().numpy()[:, 0], hm.cpu().numpy()[:, 0, :, 0].astype(np.complex128))
+    assert np.allclose(yt.cpu().numpy()[:, 0], yt_ref, atol=1e-4)
+    y = OFDMDemodulator(fft, l_min, cp)(yt)                                  # [6, 1, 2, nsym, fft]
+    hf = cir_to_ofdm_channel(subcarrier_frequencies(fft, scs), a[..., :nsym], tau)
+    yf = ApplyOFDMChannel()(x, hf)
+    err = float(((y - yf).abs() ** 2).mean() / (yf.abs() ** 2).mean())
+    assert err < 1e-2                          # sinc tails cut at l_min = -6 carry (1 / 6 pi)^2 = -25 dB of the energy
+    # convenience blocks: shapes, noise, returned channel
+    rg = ResourceGrid(nsym, fft, scs, num_tx=1, num_streams_per_tx=2, cyclic_prefix_length=cp)
+    yo, ho = OFDMChannel(tdl, rg, normalize_channel=True, return_channel=True)(x, 0.1)
+    assert list(yo.shape) == [6, 1, 2, nsym, fft] and list(ho.shape) == [6, 1, 2, 1, 2, nsym, fft]
+    yc, hc = TimeChannel(tdl, bw, n_time, maximum_delay_spread=300e-9, return_channel=True)(xt, 0.1)
+    assert list(yc.shape) == [6, 1, 2, n_time + l_tot - 1] and list(hc.shape) == [6, 1, 2, 1, 2, n_time + l_tot - 1, l_tot]
+
+
+def test_pusch_time_domain_link_over_tdl(cuda_device):
+    """PUSCHTransmitter(output_domain="time") -> TimeChannel(TDL-A, 3 m/s) -> PUSCHReceiver(input_domain="time")."""
+    from sionna_b200.phy.nr import PUSCHConfig, PUSCHTransmitter, PUSCHReceiver
+    from sionna_b200.phy.channel import TDL, TimeChannel, time_lag_discrete_time_channel
+    from sionna_b200.phy import config
+    config.seed = 31
+    pc = PUSCHConfig()
+    pc.carrier.n_size_grid = 8
+    pc.carrier.subcarrier_spacing = 30
+    pc.dmrs.additional_position = 1
+    pc.tb.mcs_index = 6
+    tx = PUSCHTransmitter(pc, output_domain="time")
+    rg = tx.resource_grid
+    l_min, l_max = time_lag_discrete_time_channel(rg.bandwidth, 300e-9)
+    rx = PUSCHReceiver(tx, input_domain="time", l_min=l_min, return_tb_crc_status=True)
+    x, b = tx(64)
+    chan = TimeChannel(TDL("A", 30e-9, 3.5e9, min_speed=3.0, num_rx_ant=4), rg.bandwidth, rg.num_time_samples,
+                       maximum_delay_spread=300e-9, normalize_channel=True)
+    y = chan(x, 0.005)
+    b_hat, crc = rx(y, 0.005)
+    assert float((b_hat != b).float().mean()) < 1e-3 and float(crc.float().mean()) > 0.98
