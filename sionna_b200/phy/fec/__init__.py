@@ -4,4 +4,4 @@ from . import utils
 from . import crc
 from . import scrambling
 from .crc import CRCEncoder, CRCDecoder
-from .scrambling import TB5GScrambler
+from .scrambling import TB5GScrambler, Scrambler, Descrambler

@@ -85,3 +85,97 @@ class TB5GScrambler(Block):
         check(lib().sb_scramble(ptr(xin), ptr(self._seq), int(binary), ptr(out), xin.numel() // self._n, self._n,
                                 len(self._c_init), current_stream()), "sb_scramble")
         return out.to(x.dtype) if x.dtype.is_floating_point else out
+
+
+class Scrambler(Block):
+    """Scrambler(seed=None, keep_batch_constant=False, binary=True, sequence=None, keep_state=True, precision=None)
+
+    Pseudo-random flipping of bits (``binary``) or of the signs of soft values (scrambling.py:20-262). ``call(x,
+    seed=None, binary=None)``: the sequence is drawn on the device from the block's seed (kept constant over calls when
+    ``keep_state``), from the ``seed`` given to the call, or from a fresh random seed; ``sequence`` overrides all of them;
+    ``keep_batch_constant`` uses one sequence for every batch sample. Scrambling twice with the same seed restores x."""
+
+    def __init__(self, seed=None, keep_batch_constant=False, binary=True, sequence=None, keep_state=True, precision=None,
+                 **kwargs):
+        super().__init__(precision=precision, **kwargs)
+        if not isinstance(keep_batch_constant, bool):
+            raise TypeError("keep_batch_constant must be bool.")
+        if seed is not None:
+            if sequence is not None:
+                print("Note: explicit scrambling sequence provided. Seed will be ignored.")
+            if not isinstance(seed, int):
+                raise TypeError("seed must be int.")
+        else:
+            from ..config import config
+            seed = int(config.np_rng.uniform(0, 2 ** 31 - 1))
+        if not isinstance(binary, bool):
+            raise TypeError("binary must be bool.")
+        if not isinstance(keep_state, bool):
+            raise TypeError("keep_state must be bool.")
+        self._keep_batch_constant, self._binary, self._keep_state, self._seed = keep_batch_constant, binary, keep_state, seed
+        self._sequence = None
+        if sequence is not None:
+            seq = np.asarray(sequence.cpu() if isinstance(sequence, torch.Tensor) else sequence, np.float32)
+            if not np.all((seq == 0) | (seq == 1)):
+                raise AssertionError("Scrambling sequence must be binary.")
+            self._sequence = seq
+
+    seed = property(lambda self: self._seed)
+    keep_state = property(lambda self: self._keep_state)
+    sequence = property(lambda self: self._sequence)
+
+    def _draw(self, shape, seed, dev):
+        """0/1 sequence of `shape` from the Philox stream keyed by (1337, seed) (scrambling.py:156-179)."""
+        seq = torch.empty(shape, dtype=torch.float32, device=dev)
+        key = ((1337 << 32) ^ (int(seed) & 0xFFFFFFFF)) & 0x7FFFFFFFFFFFFFFF
+        check(lib().sb_binary_source(ptr(seq), seq.numel(), key, 0, current_stream()), "sb_binary_source")
+        return seq
+
+    def call(self, x, seed=None, binary=None):
+        if binary is None:
+            binary = self._binary
+        elif not isinstance(binary, bool):
+            raise TypeError("binary must be bool.")
+        dev = self.device
+        xin = x.to(device=dev, dtype=torch.float32).contiguous()
+        if seed is None:
+            if self._keep_state:
+                seed = self._seed
+            else:
+                from ..config import config
+                seed = int(config.np_rng.integers(0, 2 ** 31 - 1))
+        if self._sequence is not None:
+            seq = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(self._sequence, tuple(xin.shape)))).to(dev)
+        elif self._keep_batch_constant and xin.dim() > 1:
+            seq = self._draw([1] + list(xin.shape[1:]), seed, dev)
+        else:
+            seq = self._draw(list(xin.shape), seed, dev)
+        n = seq.numel()                                         # one row of the kernel = one period of the sequence
+        out = torch.empty_like(xin)
+        check(lib().sb_scramble(ptr(xin), ptr(seq), int(binary), ptr(out), xin.numel() // n, n, 1, current_stream()),
+              "sb_scramble")
+        return out.to(x.dtype) if x.dtype.is_floating_point else out
+
+
+class Descrambler(Block):
+    """Descrambler(scrambler, binary=True, precision=None): inverse of an associated `Scrambler` / `TB5GScrambler`
+    (scrambling.py:470-579); ``call(x, seed=None)`` re-applies its sequence, typically on LLRs (``binary=False``)."""
+
+    def __init__(self, scrambler, binary=True, precision=None, **kwargs):
+        super().__init__(precision=precision, **kwargs)
+        if not isinstance(scrambler, (Scrambler, TB5GScrambler)):
+            raise TypeError("scrambler must be an instance of Scrambler.")
+        if not isinstance(binary, bool):
+            raise TypeError("binary must be bool.")
+        self._scrambler, self._binary = scrambler, binary
+        if not scrambler.keep_state:
+            print("Warning: scrambler uses random sequences that cannot be accessed by descrambler. Please use "
+                  "keep_state=True or provide explicit random seed as input to call function.")
+
+    scrambler = property(lambda self: self._scrambler)
+
+    def call(self, x, /, *, seed=None):
+        if isinstance(self._scrambler, Scrambler):
+            s = seed if seed is not None else self._scrambler.seed
+            return self._scrambler(x, seed=s, binary=self._binary)
+        return self._scrambler(x, binary=self._binary)

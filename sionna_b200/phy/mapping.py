@@ -328,3 +328,76 @@ class BinarySource(Block):
             seed, off = config.next_philox()
         check(lib().sb_binary_source(ptr(out), n, seed, off, current_stream()), "sb_binary_source")
         return out.to(self.rdtype)
+
+
+class SymbolInds2Bits(Block):
+    """SymbolInds2Bits(num_bits_per_symbol, precision=None): symbol indices -> their binary label, MSB first
+    (mapping.py:1140-1179): ``[..., n]`` int -> ``[..., n, num_bits_per_symbol]`` float."""
+
+    def __init__(self, num_bits_per_symbol, precision=None, **kwargs):
+        super().__init__(precision=precision, **kwargs)
+        m = int(num_bits_per_symbol)
+        labels = (np.arange(2 ** m)[:, None] >> np.arange(m - 1, -1, -1)) & 1
+        self._labels_np = labels.astype(np.float32)
+        self._labels = None
+
+    def call(self, symbol_ind):
+        ind = torch.as_tensor(symbol_ind).to(self.device).long()
+        if self._labels is None or self._labels.device != ind.device:
+            self._labels = torch.from_numpy(self._labels_np).to(ind.device)
+        return self._labels[ind]
+
+
+class SymbolSource(Block):
+    """SymbolSource(constellation_type=None, num_bits_per_symbol=None, constellation=None, return_indices=False, return_bits=False, seed=None, precision=None)
+
+    Random constellation symbols of the requested shape (mapping.py:1355-1445): `BinarySource` + `Mapper`. Returns
+    ``symbols`` or ``[symbols, (indices), (bits)]``."""
+
+    def __init__(self, constellation_type=None, num_bits_per_symbol=None, constellation=None, return_indices=False,
+                 return_bits=False, seed=None, precision=None, **kwargs):
+        super().__init__(precision=precision, **kwargs)
+        constellation = Constellation.check_or_create(constellation_type=constellation_type,
+                                                      num_bits_per_symbol=num_bits_per_symbol,
+                                                      constellation=constellation, precision=precision)
+        self._num_bits_per_symbol = constellation.num_bits_per_symbol
+        self._return_indices, self._return_bits = return_indices, return_bits
+        self._binary_source = BinarySource(seed=seed, precision=precision)
+        self._mapper = Mapper(constellation=constellation, return_indices=return_indices, precision=precision)
+
+    def __call__(self, inputs):
+        return self.call(inputs)
+
+    def call(self, inputs):
+        shape = [int(v) for v in (inputs.tolist() if hasattr(inputs, "tolist") else inputs)]
+        b = self._binary_source(shape + [self._num_bits_per_symbol])
+        if self._return_indices:
+            x, ind = self._mapper(b)
+        else:
+            x = self._mapper(b)
+        result = x.squeeze(-1)
+        if self._return_indices or self._return_bits:
+            result = [result]
+        if self._return_indices:
+            result.append(ind.squeeze(-1))
+        if self._return_bits:
+            result.append(b)
+        return result
+
+
+class QAMSource(SymbolSource):
+    """QAMSource(num_bits_per_symbol=None, return_indices=False, return_bits=False, seed=None, precision=None) (mapping.py:1447-1500)."""
+
+    def __init__(self, num_bits_per_symbol=None, return_indices=False, return_bits=False, seed=None, precision=None,
+                 **kwargs):
+        super().__init__(constellation_type="qam", num_bits_per_symbol=num_bits_per_symbol, return_indices=return_indices,
+                         return_bits=return_bits, seed=seed, precision=precision, **kwargs)
+
+
+class PAMSource(SymbolSource):
+    """PAMSource(num_bits_per_symbol=None, return_indices=False, return_bits=False, seed=None, precision=None) (mapping.py:1502-1555)."""
+
+    def __init__(self, num_bits_per_symbol=None, return_indices=False, return_bits=False, seed=None, precision=None,
+                 **kwargs):
+        super().__init__(constellation_type="pam", num_bits_per_symbol=num_bits_per_symbol, return_indices=return_indices,
+                         return_bits=return_bits, seed=seed, precision=precision, **kwargs)

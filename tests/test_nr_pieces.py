@@ -151,3 +151,48 @@ def test_tb_multi_stream(cuda_device):
                                                                  12000, 0.5, 4, 1, nr, ni))
     u_hat, ok = TBDecoder(enc, cn_update="minsum")(2 * c - 1)
     assert np.array_equal(u_hat.cpu().numpy(), u) and ok.shape == (4, 3) and bool(ok.all())
+
+
+@pytest.mark.gpu
+def test_scrambler_descrambler_and_symbol_sources(cuda_device):
+    """Scrambler / Descrambler (scrambling.py:20-579) and the SymbolSource family (mapping.py:1140-1555)."""
+    import torch
+    from sionna_b200.phy.fec.scrambling import Scrambler, Descrambler, TB5GScrambler
+    from sionna_b200.phy.mapping import QAMSource, PAMSource, SymbolInds2Bits, Constellation
+    from sionna_b200.phy.channel import RayleighBlockFading
+    x = (torch.rand(8, 3, 100, device=cuda_device) > 0.5).float()
+    s = Scrambler(seed=42)
+    y = s(x)
+    assert torch.equal(s(y), x) and not torch.equal(y, x)
+    assert 0.4 < float((y != x).float().mean()) < 0.6
+    assert torch.equal(Scrambler(seed=42)(x), y)                                 # seed defines the sequence
+    assert not torch.equal(Scrambler(seed=43)(x), y)
+    llr = torch.randn(8, 3, 100, device=cuda_device)
+    d = Descrambler(s, binary=False)
+    flipped = s(llr, binary=False)
+    assert torch.equal(d(flipped), llr)
+    assert torch.equal(flipped.abs(), llr.abs())
+    assert torch.equal((flipped != llr), (y != x))                                # signs flip exactly where bits flip
+    kb = Scrambler(seed=7, keep_batch_constant=True)
+    z = kb(torch.zeros(5, 64, device=cuda_device))
+    assert bool((z == z[0]).all())
+    seq = np.tile([0, 1], 50)
+    e = Scrambler(sequence=seq)(torch.zeros(4, 100, device=cuda_device))
+    assert np.array_equal(e.cpu().numpy(), np.tile(seq, (4, 1)))
+    s_rand = Scrambler(keep_state=False)
+    assert not torch.equal(s_rand(x), s_rand(x))
+    assert torch.equal(s_rand(s_rand(x, seed=5), seed=5), x)
+    t5 = TB5GScrambler(n_rnti=3, n_id=7)
+    assert torch.equal(Descrambler(t5)(t5(x)), x)
+    with pytest.raises(TypeError):
+        Descrambler("scrambler")
+    sym, ind, bits = QAMSource(4, return_indices=True, return_bits=True, seed=1)([6, 50])
+    assert list(sym.shape) == [6, 50] and list(ind.shape) == [6, 50] and list(bits.shape) == [6, 50, 4]
+    pts = Constellation("qam", 4)().cpu().numpy()
+    assert np.allclose(sym.cpu().numpy(), pts[ind.cpu().numpy()])
+    assert torch.equal(SymbolInds2Bits(4)(ind), bits)
+    p = PAMSource(3)([1000])
+    assert p.is_complex() and float(p.imag.abs().max()) == 0.0 and abs(float((p.abs() ** 2).mean()) - 1.0) < 0.1
+    a, tau = RayleighBlockFading(1, 4, 2, 1)(256, 14)
+    assert list(a.shape) == [256, 1, 4, 2, 1, 1, 14] and list(tau.shape) == [256, 1, 2, 1]
+    assert bool((a == a[..., :1]).all()) and abs(float((a.abs() ** 2).mean()) - 1.0) < 0.1
