@@ -158,3 +158,43 @@ def test_qc_description_accepted_and_rejected():
         assert not dec._graph.set_qc(enc.z, br, bc, bad)      # wrong shift -> rejected, handle keeps the valid one
         assert dec._graph.is_qc()
         assert not dec._graph.set_qc(enc.z, br[:-1], bc[:-1], sh[:-1]) or dec.num_cns < 46 * enc.z
+
+
+def test_channel_host_logic():
+    """TDL model tables / derived properties and the discrete-time lag rule (no device needed)."""
+    from sionna_b200.phy.channel import TDL, time_lag_discrete_time_channel
+    from sionna_b200.phy.channel.tdl import subcarrier_frequencies
+    t = TDL("A", 300e-9, 3.5e9)
+    assert t.num_clusters == 23 and not t.los
+    assert abs(float(t.mean_powers.sum()) - 1.0) < 1e-6
+    assert abs(float(t.delays[-1]) - 9.6586 * 300e-9) < 1e-12          # TR 38.901 Table 7.7.2-1, last tap
+    d = TDL("D", 100e-9, 3.5e9, min_speed=1.0, max_speed=2.0)
+    assert d.los and d.num_clusters == 13
+    assert abs(10 * np.log10(d.k_factor) - 13.3) < 0.05                  # K-factor of TDL-D
+    assert abs(float(d.mean_powers.sum()) - 1.0) < 1e-6
+    assert abs(d._doppler(3.0) - 2 * np.pi * 3.0 / 299792458.0 * 3.5e9) < 1e-9
+    c = TDL("C300", 10e-9, 3.5e9)                                        # fixed-delay model: delay spread forced
+    assert c.delay_spread == 300e-9 and abs(float(c.delays[-1]) - 2595e-9) < 1e-12
+    with pytest.raises(AssertionError):
+        TDL("Z", 1e-7, 3.5e9)
+    with pytest.raises(AssertionError):
+        TDL("A", 1e-7, 3.5e9, min_speed=5.0, max_speed=1.0)
+    assert time_lag_discrete_time_channel(30.72e6) == (-6, int(np.ceil(3e-6 * 30.72e6)) + 6)
+    f = subcarrier_frequencies(5, 15e3).numpy()
+    assert np.array_equal(f, np.array([-2, -1, 0, 1, 2]) * 15e3)
+    f = subcarrier_frequencies(4, 15e3).numpy()
+    assert np.array_equal(f, np.array([-2, -1, 0, 1]) * 15e3)
+
+
+def test_separable_constellation_detection():
+    """The per-dimension demapper is only selected for constellations that factor exactly (oracle twin of the host rule)."""
+    from oracle import mapping as M
+    for m in (2, 4, 6, 8, 10):
+        lev = M.separable_levels(M.qam(m))
+        assert lev is not None and len(lev[0]) == 2 ** (m // 2)
+        pts = M.qam(m)
+        assert M.separable_levels(pts * np.exp(1j * 0.1)) is None          # rotated: not separable
+    assert M.separable_levels(M.pam(3)) is None                              # odd number of bits
+    pts = M.qam(4).copy()
+    pts[5] += 0.01
+    assert M.separable_levels(pts) is None                                   # perturbed (e.g. trained) constellation

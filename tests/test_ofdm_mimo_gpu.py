@@ -15,7 +15,7 @@ def _c64(rng, shape, scale=1.0):
     return ((rng.normal(size=shape) + 1j * rng.normal(size=shape)) * scale / np.sqrt(2)).astype(np.complex64)
 
 
-@pytest.mark.parametrize("n", [72, 76, 64, 128, 180, 1024, 4096, 19, 600])
+@pytest.mark.parametrize("n", [72, 76, 64, 128, 180, 1024, 4096, 19, 600, 2048, 1536, 3276])
 def test_ofdm_mod_demod_vs_oracle(cuda_device, n):
     from sionna_b200.phy.ofdm import OFDMModulator, OFDMDemodulator
     rng = np.random.default_rng(n)
