@@ -44,6 +44,24 @@ def cir_to_time_channel(bandwidth, a, tau, l_min, l_max, normalize=False):
     return hm
 
 
+def time_to_ofdm_channel(h_t, rg, l_min):
+    """Frequency response seen by each OFDM symbol from time-domain taps (utils.py:352-458): the taps at the first
+    sample after every cyclic prefix, zero-padded to ``fft_size``, rolled by ``l_min``, un-normalised DFT + fftshift
+    (``sb_ofdm_demodulate`` with the shift folded in). ``h_t [..., num_time_samples + l_tot - 1, l_tot]`` ->
+    ``[..., num_ofdm_symbols, fft_size]``."""
+    n = rg.fft_size
+    ofdm_length = n + rg.cyclic_prefix_length
+    h = h_t[..., rg.cyclic_prefix_length:rg.num_time_samples:ofdm_length, :].to(torch.complex64)
+    h = torch.cat([h, torch.zeros(list(h.shape[:-1]) + [n - h.shape[-1]], dtype=h.dtype, device=h.device)], -1)
+    h = torch.roll(h, int(l_min), dims=-1).contiguous()
+    rows = h.numel() // n
+    zero = torch.zeros(1, dtype=torch.int32, device=h.device)
+    out = torch.empty_like(h)
+    check(lib().sb_ofdm_demodulate(ptr(h), ptr(out), rows, 1, n, ptr(zero), ptr(zero), n, 0, 1, current_stream()),
+          "sb_ofdm_demodulate")
+    return out * float(np.sqrt(n))                            # the kernel applies 1 / sqrt(N); tf.signal.fft does not
+
+
 class ApplyTimeChannel(Block):
     """ApplyTimeChannel(num_time_samples, l_tot, precision=None): ``call(x, h_time, no=None)`` filters
     ``x [batch, num_tx, num_tx_ant, num_time_samples]`` with the time-variant taps ``h_time [batch, num_rx, num_rx_ant,

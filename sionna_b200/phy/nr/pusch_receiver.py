@@ -14,8 +14,8 @@ class PUSCHReceiver(Block):
     """PUSCHReceiver(pusch_transmitter, channel_estimator=None, mimo_detector=None, tb_decoder=None, return_tb_crc_status=False, stream_management=None, input_domain="freq", l_min=None, precision=None)
 
     ``call(y, no, h=None)``: optional `OFDMDemodulator` (``input_domain="time"``) -> channel estimation
-    (`PUSCHLSChannelEstimator` with linear interpolation by default; ``"perfect"`` uses the provided ``h``, multiplied by
-    the precoding matrices when the transmitter precodes) -> MIMO detection (default LMMSE `LinearDetector`, max-log
+    (`PUSCHLSChannelEstimator` with linear interpolation by default; ``"perfect"`` uses the provided ``h`` -- time-domain
+    taps are converted with `time_to_ofdm_channel` -- multiplied by the precoding matrices when the transmitter precodes) -> MIMO detection (default LMMSE `LinearDetector`, max-log
     bit LLRs) -> `LayerDemapper` -> `TBDecoder`. Returns ``b_hat [batch, num_tx, tb_size]`` (and ``tb_crc_status
     [batch, num_tx]`` if ``return_tb_crc_status``)."""
 
@@ -67,7 +67,8 @@ class PUSCHReceiver(Block):
         if self._perfect_csi:
             assert h is not None, "h must be provided for channel_estimator='perfect'"
             if self._input_domain == "time":
-                raise NotImplementedError("perfect CSI in the time domain (time_to_ofdm_channel) is not provided")
+                from ..channel import time_to_ofdm_channel
+                h = time_to_ofdm_channel(h, self.resource_grid, self._l_min)
             if self._w is not None:
                 # effective channel per layer: h_eff[b, r, ra, t, l, s, f] = sum_p h[b, r, ra, t, p, s, f] W[t, p, l]
                 h = torch.einsum("bratpsf,tpl->bratlsf", h.to(torch.complex64), self._w.w)

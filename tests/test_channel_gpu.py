@@ -126,6 +126,11 @@ def test_time_channel_vs_oracle_and_ofdm_equivalence(cuda_device):
     yf = ApplyOFDMChannel()(x, hf)
     err = float(((y - yf).abs() ** 2).mean() / (yf.abs() ** 2).mean())
     assert err < 1e-2                          # sinc tails cut at l_min = -6 carry (1 / 6 pi)^2 = -25 dB of the energy
+    from sionna_b200.phy.channel import time_to_ofdm_channel
+    rg0 = ResourceGrid(nsym, fft, scs, cyclic_prefix_length=cp)
+    hf_t = time_to_ofdm_channel(hm, rg0, l_min)                               # [6, 1, 2, 1, 2, nsym, fft]
+    assert list(hf_t.shape) == list(hf.shape)
+    assert float(((hf_t - hf).abs() ** 2).mean() / (hf.abs() ** 2).mean()) < 1e-2
     # convenience blocks: shapes, noise, returned channel
     rg = ResourceGrid(nsym, fft, scs, num_tx=1, num_streams_per_tx=2, cyclic_prefix_length=cp)
     yo, ho = OFDMChannel(tdl, rg, normalize_channel=True, return_channel=True)(x, 0.1)
@@ -155,3 +160,9 @@ def test_pusch_time_domain_link_over_tdl(cuda_device):
     y = chan(x, 0.005)
     b_hat, crc = rx(y, 0.005)
     assert float((b_hat != b).float().mean()) < 1e-3 and float(crc.float().mean()) > 0.98
+    # perfect CSI from the time-domain taps (time_to_ofdm_channel inside the receiver)
+    chan_h = TimeChannel(TDL("A", 30e-9, 3.5e9, num_rx_ant=4), rg.bandwidth, rg.num_time_samples,
+                         maximum_delay_spread=300e-9, normalize_channel=True, return_channel=True)
+    y2, h_time = chan_h(x, 0.005)
+    rx_p = PUSCHReceiver(tx, channel_estimator="perfect", input_domain="time", l_min=l_min)
+    assert float((rx_p(y2, 0.005, h_time) != b).float().mean()) < 1e-3
