@@ -48,34 +48,59 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock and throttle reasons while the timed region runs: NVML (`pynvml`, ~20 ms period) when it is
+    importable, else `nvidia-smi` polling (the recipe's clocks line, ~5 samples/s)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()   # samples: (sm_mhz, max_mhz, set(reasons))
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._halt.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append((int(sm), int(mx), {n for n, m in masks.items() if bits & m}))
+            self._halt.wait(0.02)
+        nv.nvmlShutdown()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                f = [v.strip() for v in out.split(",")]
+                if len(f) >= 6 and f[0].isdigit() and f[1].isdigit():
+                    self.samples.append((int(f[0]), int(f[1]),
+                                         {n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")}))
             except Exception:
                 pass
             self._halt.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                "reasons": sorted(set().union(*[s[2] for s in self.samples])) if self.samples else [],
+                "samples": len(sm)}
 
 
 def make_inputs(seed, batch, device=None):

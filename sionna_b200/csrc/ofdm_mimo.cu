@@ -19,6 +19,7 @@
 // All kernels are one pass over HBM; FFT twiddles come from sincospif (<= 1 ulp), parity bar 1e-5 (the reference's own
 // round-trip test tolerance, test/unit/ofdm/test_ofdm.py:85-96).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "sb_common.h"
 #include <map>
@@ -841,11 +842,18 @@ int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* c
     SmallFftPlan sp;
     int rc = get_small_plan(n, &sp);
     if (rc) return rc;
-    // transforms per warp: as many as keep two CTAs' buffers on an SM
-    if (n <= 128) return launch_fft_small_fpw<DEMOD, 4>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
-    if (n <= 384) return launch_fft_small_fpw<DEMOD, 2>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
+    // transforms per warp: as many as keep two CTAs' buffers on an SM (SB_FFT_FPW overrides, for experiments)
+    int fpw = n <= 128 ? 4 : (n <= 384 ? 2 : 1);
+    if (const char* e = getenv("SB_FFT_FPW")) {
+        int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && (size_t)n * 8 * (2 + 16 * v) <= 160 * 1024) fpw = v;
+    }
+    if (fpw == 8) return launch_fft_small_fpw<DEMOD, 8>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
+    if (fpw == 4) return launch_fft_small_fpw<DEMOD, 4>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
+    if (fpw == 2) return launch_fft_small_fpw<DEMOD, 2>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
     return launch_fft_small_fpw<DEMOD, 1>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
 }
+
 }  // namespace
 
 extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, int32_t num_symbols, int32_t fft_size,
