@@ -842,7 +842,8 @@ int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* c
     SmallFftPlan sp;
     int rc = get_small_plan(n, &sp);
     if (rc) return rc;
-    // transforms per warp: as many as keep two CTAs' buffers on an SM (SB_FFT_FPW overrides, for experiments)
+    // transforms per warp (SB_FFT_FPW overrides, for experiments). Measured at N = 76: 1 -> 0.82 ms, 4 -> 0.55 ms,
+    // 8 -> 0.63 ms per 458 k transforms (8 halves the resident warps per SM).
     int fpw = n <= 128 ? 4 : (n <= 384 ? 2 : 1);
     if (const char* e = getenv("SB_FFT_FPW")) {
         int v = atoi(e);
