@@ -15,9 +15,11 @@ def build(force=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     # -ffp-contract=off: fp32 operations stay separately rounded like the reference's TF ops (and like the
     # CUDA kernels, built with -fmad=false); -mfma only makes the explicit fmaf() calls of sb_math.h fast.
+    tmp = f"{OUT}.tmp.{os.getpid()}"                        # atomic publish (several ranks may build at once)
     cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-mfma",
-           "-fno-fast-math", "-o", OUT] + srcs + ["-lm"]
+           "-fno-fast-math", "-o", tmp] + srcs + ["-lm"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -10,7 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "..", "libsionna_b200.so")
 SOURCES = ["common.cu", "ldpc_bp.cu", "ldpc_bp_qc.cu", "ldpc_enc.cu", "phy_kernels.cu", "ofdm_mimo.cu"]
-HEADERS = ["sb_common.h", "sb_math.h", "rng.cuh", "ldpc_graph.h", os.path.join("..", "..", "include", "sionna_b200.h")]
+HEADERS = ["sb_common.h", "sb_math.h", "sb_math2.cuh", "sb_logtab.h", "rng.cuh", "ldpc_graph.h",
+           os.path.join("..", "..", "include", "sionna_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # never contract a*b+c implicitly: parity with the CPU oracle is bit-exact
@@ -34,12 +35,16 @@ def build(force=False, verbose=False):
     if not force and not _stale(lib, deps):
         return lib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", lib] + srcs
+    tmp = f"{lib}.tmp.{os.getpid()}"                        # atomic publish: concurrent builders (one per rank) cannot
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + srcs          # expose a half-written library
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libsionna_b200.so")
+    os.replace(tmp, lib)
     with open(os.path.join(HERE, "..", "build_ptxas.log"), "w") as f:
         f.write(res.stdout + res.stderr)
     return lib
