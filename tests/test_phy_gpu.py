@@ -55,7 +55,7 @@ def test_mapper_exact(cuda_device, m):
 
 
 @pytest.mark.parametrize("method", ["app", "maxlog"])
-@pytest.mark.parametrize("m", [2, 4, 6])
+@pytest.mark.parametrize("m", [2, 4, 6, 8, 10])
 def test_demapper_vs_oracle(cuda_device, m, method):
     from sionna_b200.phy.mapping import Demapper
     rng = np.random.default_rng(10 + m)
@@ -87,6 +87,29 @@ def test_demapper_vs_oracle(cuda_device, m, method):
                           M.demapper(y, np.float32(no), pts, method, prior=p1, math_mode=1))
     hard = Demapper(method, "qam", m, hard_out=True)(yd, no).cpu().numpy()
     assert np.array_equal(hard, (llr > 0).astype(np.float32))
+
+
+@pytest.mark.parametrize("method", ["app", "maxlog"])
+def test_demapper_generic_constellations_vs_oracle(cuda_device, method):
+    """Non-separable constellations (PAM, rotated / custom points) take the 2-D kernel: bit-exact vs the oracle's
+    reference-order formula in kernel math; the separable kernel and the 2-D kernel agree to rounding on square QAM."""
+    from sionna_b200.phy.mapping import Demapper, Constellation
+    rng = np.random.default_rng(77)
+    no = np.float32(0.15)
+    for name, pts in (("pam3", M.pam(3)), ("rot16", (M.qam(4) * np.exp(0.3j)).astype(np.complex64)),
+                      ("qam7bits", (rng.normal(size=128) + 1j * rng.normal(size=128)).astype(np.complex64))):
+        m = int(np.log2(len(pts)))
+        assert M.separable_levels(pts) is None
+        const = Constellation("pam", 3) if name == "pam3" else Constellation("custom", m, points=pts)
+        y = (rng.normal(size=(5, 64)) + 1j * rng.normal(size=(5, 64))).astype(np.complex64)
+        llr = Demapper(method, constellation=const)(torch.from_numpy(y).to(cuda_device), float(no)).cpu().numpy()
+        assert np.array_equal(llr, M.demapper(y, no, const().cpu().numpy(), method, math_mode=1)), name
+    # square QAM through BOTH kernels: a custom constellation holding the same points but perturbed by nothing
+    pts = M.qam(6)
+    y = (rng.normal(size=(4, 100)) + 1j * rng.normal(size=(4, 100))).astype(np.complex64)
+    sep = Demapper(method, "qam", 6)(torch.from_numpy(y).to(cuda_device), float(no)).cpu().numpy()
+    ref2d = M.demapper(y, no, pts, method, math_mode=0)                       # the reference's 2-D formula, libm
+    np.testing.assert_allclose(sep, ref2d, rtol=1e-4, atol=1e-4)
 
 
 def test_awgn_and_sources(cuda_device):
