@@ -71,3 +71,44 @@ def test_lmmse_noiseless_and_statistics():
     assert abs(np.var(err) - np.mean(no_eff)) / np.mean(no_eff) < 3e-2
     x0, ne0 = F.lmmse_equalizer((h @ x[..., None])[..., 0], h, np.broadcast_to(1e-9 * np.eye(m), (num, m, m)))
     assert np.abs(x0 - x).max() < 1e-5 and ne0.max() < 1e-6
+
+
+def test_oracle_channel_generation_restatements():
+    """oracle.ofdm.tdl_sos / cir_to_ofdm / cir_to_time / apply_time_channel against independent closed forms."""
+    rng = np.random.default_rng(4)
+    b, a_pairs, p, ns, t_steps, fs = 3, 2, 4, 20, 6, 1e4
+    powers = np.array([0.5, 0.3, 0.15, 0.05])
+    theta = rng.uniform(-np.pi / ns, np.pi / ns, (b, p, ns))
+    phi = rng.uniform(-np.pi, np.pi, (b, a_pairs, p, ns))
+    # zero Doppler: the taps do not depend on time and equal sqrt(P / Ns) * sum_n exp(j phi_n)
+    a0 = F.tdl_sos(np.zeros(b), theta, phi, None, powers, 0.0, 0.0, t_steps, fs)
+    want = np.sqrt(powers / ns)[None, None, :] * np.exp(1j * phi).sum(-1)
+    assert np.allclose(a0, want[..., None]) and a0.shape == (b, a_pairs, p, t_steps)
+    # one sinusoid, no angle jitter: a pure complex exponential at w cos(2 pi / 1)
+    w = np.array([200.0, 300.0, 0.0])
+    a1 = F.tdl_sos(w, np.zeros((b, 1, 1)), np.zeros((b, 1, 1, 1)), None, np.array([1.0]), 0.0, 0.0, t_steps, fs)
+    tt = np.arange(t_steps) / fs
+    assert np.allclose(a1[:, 0, 0, :], np.exp(1j * w[:, None] * tt[None, :] * np.cos(2 * np.pi)))
+    # LoS term on the first path only
+    phi0 = rng.uniform(-np.pi, np.pi, b)
+    a2 = F.tdl_sos(w, theta, phi, phi0, powers, 0.7, np.pi / 4, t_steps, fs)
+    base = F.tdl_sos(w, theta, phi, None, powers, 0.0, 0.0, t_steps, fs)
+    spec = np.sqrt(0.7) * np.exp(1j * (w[:, None] * tt[None, :] * np.cos(np.pi / 4) + phi0[:, None]))
+    assert np.allclose(a2[:, :, 0, :] - base[:, :, 0, :], spec[:, None, :]) and np.allclose(a2[:, :, 1:], base[:, :, 1:])
+    # a single path with delay tau: frequency response exp(-j 2 pi f tau), time response sinc(l - tau W)
+    freqs = (np.arange(16) - 8) * 15e3
+    tau = np.array([2.5e-6])
+    h = F.cir_to_ofdm(freqs, np.ones((1, 1, 3), complex), tau)
+    assert np.allclose(h[0], np.exp(-2j * np.pi * freqs * tau[0])[None, :].repeat(3, 0))
+    bw = 16 * 15e3
+    ht = F.cir_to_time(bw, np.ones((1, 1, 3), complex), np.array([3 / bw]), -2, 5)       # integer delay of 3 samples
+    assert np.allclose(ht[0, 0], (np.arange(-2, 6) == 3).astype(float), atol=1e-12)
+    # time-variant filtering with constant taps is a plain convolution
+    x = rng.normal(size=(2, 2, 10)) + 1j * rng.normal(size=(2, 2, 10))
+    taps = rng.normal(size=(2, 3, 2, 4)) + 1j * rng.normal(size=(2, 3, 2, 4))            # [B, R, Tt, L]
+    hfull = np.broadcast_to(taps[:, :, :, None, :], (2, 3, 2, 13, 4))
+    y = F.apply_time_channel(x, hfull)
+    for bb in range(2):
+        for r in range(3):
+            want = sum(np.convolve(x[bb, t], taps[bb, r, t]) for t in range(2))
+            assert np.allclose(y[bb, r], want)

@@ -324,3 +324,23 @@ def test_pusch_link_end_to_end(cuda_device, scenario):
     assert b_hat.shape == b.shape
     assert torch.equal(b_hat, b)
     assert bool(crc.all())
+
+
+def test_oracle_pusch_ls_combine_closed_form():
+    """oracle.nr.pusch_ls_combine on hand-made inputs: two ports of one CDM group with w_f = (+,+) / (+,-) are separated by
+    the pairwise average; double-symbol DMRS additionally averages the two symbols; zero entries stay zero."""
+    from oracle import nr as ON
+    h0, h1 = 1.0 + 2.0j, -0.5 + 0.25j                        # the channels of port 0 and port 1
+    # single-symbol DMRS, 2 CDM groups without data -> groups of n = 4 masked REs, ports occupy entries (0, 2) of each
+    y = np.array([h0 + h1, 0, h0 - h1, 0, h0 + h1, 0, h0 - h1, 0])        # LS estimates seen through port 0's pilots
+    out, err = ON.pusch_ls_combine(y[None], np.ones((1, 8)), 1, 1, 2)
+    assert np.allclose(out[0], [h0, 0, h0, 0, h0, 0, h0, 0]) and np.allclose(err, 0.5)
+    # port 1's pilots carry w_f = (+, -): the LS division turns the second entry into -(h0 - h1) ... = h1 - h0
+    y1 = np.array([h0 + h1, 0, -(h0 - h1), 0])
+    out1, _ = ON.pusch_ls_combine(y1[None], np.ones((1, 4)), 1, 1, 2)
+    assert np.allclose(out1[0], [h1, 0, h1, 0])
+    # double-symbol DMRS: two symbols of 4 REs each are averaged first, error variance / 4 in total
+    ys = np.concatenate([y[:4] + 0.1, y[:4] - 0.1])
+    ys[[1, 3, 5, 7]] = 0
+    out2, err2 = ON.pusch_ls_combine(ys[None], np.ones((1, 8)), 2, 2, 2)
+    assert np.allclose(out2[0], [h0, 0, h0, 0, h0, 0, h0, 0]) and np.allclose(err2, 0.25)
