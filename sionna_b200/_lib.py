@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsionna_b200.so")
+# SIONNA_B200_LIB selects another build of the same sources (A/B experiments of kernel variants)
+LIB_PATH = os.environ.get("SIONNA_B200_LIB") or os.path.join(_HERE, "libsionna_b200.so")
 _lib = None
 
 i32, i64, u64, f32, vp, sz = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
