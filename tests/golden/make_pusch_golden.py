@@ -4,6 +4,8 @@ Sources (all produced by an independent 5G toolbox and shipped with the referenc
   * test/unit/nr/pusch_test_configs/test_{0..82}.{json,npy}: PUSCH configuration, payload bits b and the complete
     transmit resource grid (used by test_pusch_transmitter.py:tests_against_reference).
   * test/unit/nr/reference_dmrs_{1,2}.npy: DMRS sequences (test_pusch_config.py:test_against_reference_{1,2}).
+  * test/unit/nr/pusch_dmrs_precoded_{L}_layer_{P}_ports.npy: precoded DMRS grids for every TPMI of the six codebooks
+    (test_pusch_config.py:test_precoding_against_reference); stored as complex64 arrays [num_tpmi, ports, 12, 14].
 
 The 83 grids are 80 MB of complex128. Stored here per case: the configuration, the payload (bit-packed), NPROJ seeded
 random linear functionals of the grid (a 64-number fingerprint that any wrong resource element changes), and for the
@@ -50,6 +52,9 @@ def main():
     out["configs_json"] = np.frombuffer(json.dumps(cfgs).encode(), np.uint8)
     for k in (1, 2):
         out[f"reference_dmrs_{k}"] = np.load(f"{REF}/reference_dmrs_{k}.npy").astype(np.complex64)
+    for layers, ports in ((1, 2), (1, 4), (2, 2), (2, 4), (3, 4), (4, 4)):
+        a = np.load(f"{REF}/pusch_dmrs_precoded_{layers}_layer_{ports}_ports.npy", allow_pickle=True)
+        out[f"dmrs_precoded_{layers}_{ports}"] = np.stack([np.asarray(v) for v in a]).astype(np.complex64)
     np.savez_compressed(OUT, **out)
     print(OUT, os.path.getsize(OUT) / 1e6, "MB")
 

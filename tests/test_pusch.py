@@ -344,3 +344,32 @@ def test_oracle_pusch_ls_combine_closed_form():
     ys[[1, 3, 5, 7]] = 0
     out2, err2 = ON.pusch_ls_combine(ys[None], np.ones((1, 8)), 2, 2, 2)
     assert np.allclose(out2[0], [h0, 0, h0, 0, h0, 0, h0, 0]) and np.allclose(err2, 0.25)
+
+
+def test_precoded_dmrs_match_reference_vectors(gold):
+    """PUSCHConfig.dmrs_grid_precoded for every TPMI of the six codebooks (TS 38.211 Tables 6.3.1.5-1..7) vs the
+    reference's stored grids (test_pusch_config.py:169-230): pins the extracted codebook tables and the DMRS port mapping."""
+    from sionna_b200.phy.nr import PUSCHConfig
+    pc = PUSCHConfig()
+    pc.carrier.n_size_grid = 1
+    pc.carrier.slot_number = 1
+    pc.dmrs.additional_position = 0
+    pc.dmrs.config_type = 2
+    pc.dmrs.num_cdm_groups_without_data = 3
+    pc.dmrs.length = 2
+    pc.dmrs.n_id = [8, 8]
+    pc.precoding = "codebook"
+    total = 0
+    for layers, ports in ((1, 2), (1, 4), (2, 2), (2, 4), (3, 4), (4, 4)):
+        if ports >= pc.num_layers:                               # keep num_layers <= num_antenna_ports at every step
+            pc.num_antenna_ports = ports
+            pc.num_layers = layers
+        else:
+            pc.num_layers = layers
+            pc.num_antenna_ports = ports
+        ref = gold[f"dmrs_precoded_{layers}_{ports}"]
+        for tpmi in range(ref.shape[0]):
+            pc.tpmi = tpmi
+            assert np.allclose(pc.dmrs_grid_precoded / np.sqrt(3), ref[tpmi], atol=1e-6), (layers, ports, tpmi)
+            total += 1
+    assert total == 6 + 28 + 3 + 22 + 7 + 5
