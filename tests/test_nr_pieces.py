@@ -196,3 +196,53 @@ def test_scrambler_descrambler_and_symbol_sources(cuda_device):
     a, tau = RayleighBlockFading(1, 4, 2, 1)(256, 14)
     assert list(a.shape) == [256, 1, 4, 2, 1, 1, 14] and list(tau.shape) == [256, 1, 2, 1]
     assert bool((a == a[..., :1]).all()) and abs(float((a.abs() ** 2).mean()) - 1.0) < 0.1
+
+
+def test_decode_mcs_index_vs_reference_known_answers():
+    """decode_mcs_index vs the 11 known-answer lists of the reference's tests (test_nr_utils.py:17-268; TS 38.214 Tables
+    5.1.3.1-1..4, 6.1.4.1-1/2 incl. the pi/2-BPSK rows); the first index past each list is invalid."""
+    import json
+    from sionna_b200.phy.nr import decode_mcs_index
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mcs_golden.json")) as f:
+        cases = json.load(f)
+    assert len(cases) == 11
+    for c in cases:
+        kw = dict(c["kwargs"])
+        variants = (True, False) if kw.get("pi2bpsk") == "both" else (kw["pi2bpsk"],)
+        for bpsk in variants:
+            kw["pi2bpsk"] = bpsk
+            for idx, (q, r) in enumerate(zip(c["qs"], c["rs"])):
+                m, rate = decode_mcs_index(mcs_index=idx, **kw)
+                assert m == q and float(rate) == np.float32(r / 1024), (kw, idx)
+            if len(c["qs"]) < 29:
+                with pytest.raises(AssertionError):
+                    decode_mcs_index(mcs_index=len(c["qs"]), **kw)
+    # vectorised call, mixed tables / channels
+    m, r = decode_mcs_index([0, 27, 5], [1, 2, 3], [True, False, True])
+    assert list(m) == [2, 8, 2] and np.allclose(r, [120 / 1024, 948 / 1024, 99 / 1024])
+
+
+def test_calculate_tb_size_consistency_sweep():
+    """The structural invariants the reference checks over a parameter sweep (test_nr_utils.py:300-374)."""
+    from sionna_b200.phy.nr import calculate_tb_size, decode_mcs_index
+    for mcs_index in (0, 4, 16, 20, 27):
+        q, r = decode_mcs_index(mcs_index, 2)
+        for num_layers in (1, 2, 3, 4):
+            for num_prbs in (1, 20, 200, 275):
+                for num_ofdm_symbols in (8, 10, 14):
+                    for num_dmrs_per_prb in (0, 10, 20):
+                        tb, cb, ncb, tb_crc, cb_crc, cw = calculate_tb_size(
+                            target_coderate=r, modulation_order=q, num_layers=num_layers, num_prbs=num_prbs,
+                            num_ofdm_symbols=num_ofdm_symbols, num_dmrs_per_prb=num_dmrs_per_prb)
+                        cw = np.asarray(cw)
+                        assert tb == ncb * (cb - cb_crc) - tb_crc and ncb == len(cw)
+                        assert cb_crc == (0 if ncb == 1 else 24)
+                        assert set(cw.tolist()) <= {int(cw.min()), int(cw.max())}
+                        assert tb_crc == (24 if tb > 3824 else 16)
+                        n_res = q * num_layers * (12 * num_ofdm_symbols - num_dmrs_per_prb)
+                        if n_res <= 156:
+                            eff = tb / cw.sum()
+                            if tb > 4000:
+                                assert abs(eff - r) < 2e-2
+                            elif tb > 200:
+                                assert abs(eff - r) < 1e-1
