@@ -27,6 +27,23 @@ def test_crc_oracle_and_generator_rows_vs_reference_vectors():
             assert np.array_equal(par, R.crc_parity(b, pol))
 
 
+def test_prng_sequence_known_answer_of_the_reference():
+    """Gold sequence (product host code and oracle) vs the reference's 100-bit known answer (test_nr_utils.py:280-296);
+    invalid arguments are rejected as there (:273-278)."""
+    import json
+    from sionna_b200.phy.fec.scrambling import generate_prng_seq
+    with open(os.path.join(os.path.dirname(__file__), "golden", "prng_golden.json")) as f:
+        g = json.load(f)
+    c_init = g["n_rnti"] * 2 ** 15 + g["n_id"]
+    ref = np.array(g["s_ref"], float)
+    assert np.array_equal(generate_prng_seq(g["l"], c_init), ref)
+    assert np.array_equal(R.generate_prng_seq(g["l"], c_init), ref)
+    assert not np.array_equal(generate_prng_seq(g["l"], c_init + 1), ref)
+    for bad in ([-1, 10], [10, -1], [100, 2 ** 32], [10.2, 10], [10, 10.2]):
+        with pytest.raises(AssertionError):
+            generate_prng_seq(bad[0], bad[1])
+
+
 def test_prng_sequence_matches_literal_restatement():
     from sionna_b200.phy.fec.scrambling import generate_prng_seq, TB5GScrambler
     for c_init in (0, 1, 1000, 2 ** 31 - 1, 12345678):
