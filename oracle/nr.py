@@ -111,7 +111,12 @@ def tb_encode(u, num_coded_bits, target_coderate, m, num_layers, n_rnti, n_id, s
 
 # ---- PUSCH (SURVEY.md 8(f2)) -----------------------------------------------------------------------------------------
 def layer_map(x, num_layers):
-    """[..., n] -> [..., num_layers, n / num_layers], symbol i to layer i mod num_layers (layer_mapping.py:176-181,199)."""
+    """[..., n] -> [..., num_layers, n / num_layers], symbol i to layer i mod num_layers (layer_mapping.py:176-181,199).
+    5..8 layers (dual codeword mode, :182-198): `x` is a pair of codewords; the first takes floor(num_layers / 2) layers."""
+    if num_layers > 4:
+        l0 = num_layers // 2
+        y0, y1 = layer_map(np.asarray(x[0]), l0), layer_map(np.asarray(x[1]), num_layers - l0)
+        return np.concatenate([y0, y1], axis=-2)
     n = x.shape[-1]
     return np.swapaxes(x.reshape(x.shape[:-1] + (n // num_layers, num_layers)), -1, -2)
 

@@ -373,3 +373,29 @@ def test_precoded_dmrs_match_reference_vectors(gold):
             assert np.allclose(pc.dmrs_grid_precoded / np.sqrt(3), ref[tpmi], atol=1e-6), (layers, ports, tpmi)
             total += 1
     assert total == 6 + 28 + 3 + 22 + 7 + 5
+
+
+def test_layer_mapper_known_answers():
+    """LayerMapper for 1..8 layers vs the reference's predefined sequences (test_layer_mapper.py:14-203): the oracle and
+    the product's `call` (pure tensor reshapes, run here on CPU tensors); LayerDemapper inverts it."""
+    import json
+    import torch
+    from oracle import nr as ON
+    from sionna_b200.phy.nr import LayerMapper, LayerDemapper
+    with open(os.path.join(os.path.dirname(__file__), "golden", "layer_mapper_golden.json")) as f:
+        cases = json.load(f)
+    assert [c["num_layers"] for c in cases] == list(range(1, 9))
+    for c in cases:
+        nl, want = c["num_layers"], np.array(c["out"])
+        ins = [np.array(v) for v in c["inputs"]]
+        got = ON.layer_map(ins[0] if nl <= 4 else ins, nl)
+        assert np.array_equal(got, want), nl
+        lm = LayerMapper(nl)
+        t_in = torch.from_numpy(ins[0]).float() if nl <= 4 else [torch.from_numpy(v).float() for v in ins]
+        y = lm.call(t_in)
+        assert np.array_equal(y.numpy(), want), nl
+        back = LayerDemapper(lm, 1).call(y)
+        if nl <= 4:
+            assert np.array_equal(back.numpy(), ins[0])
+        else:
+            assert np.array_equal(back[0].numpy(), ins[0]) and np.array_equal(back[1].numpy(), ins[1])
