@@ -399,3 +399,52 @@ def test_layer_mapper_known_answers():
             assert np.array_equal(back.numpy(), ins[0])
         else:
             assert np.array_equal(back[0].numpy(), ins[0]) and np.array_equal(back[1].numpy(), ins[1])
+
+
+def _pusch_estimation_case(num_layers, length, additional_position, config_type, groups, rng, no=None):
+    """One configuration of the reference's estimator sweep (test_channel_estimation.py:67-111) on the CPU: host
+    configuration + oracle LS / CDM de-spreading / nearest-neighbour interpolation on a block-constant channel."""
+    from sionna_b200.phy.nr import PUSCHConfig, PUSCHPilotPattern
+    from oracle import ofdm as OO, nr as ON
+    pc = PUSCHConfig(num_layers=num_layers, num_antenna_ports=num_layers)
+    pc.n_size_bwp = 4
+    pc.dmrs.length = length
+    pc.dmrs.additional_position = additional_position
+    pc.dmrs.config_type = config_type
+    pc.dmrs.num_cdm_groups_without_data = groups
+    pp = PUSCHPilotPattern(pc)
+    mask, pilots = pp.mask.astype(bool), pp.pilots
+    n_ant, batch = 3, 4
+    chan = rng.standard_normal((batch, 1, n_ant, 1, num_layers)) + 1j * rng.standard_normal((batch, 1, n_ant, 1, num_layers))
+    x = (rng.integers(0, 2, (batch, 1, num_layers, 14, 48)) * 2 - 1) / np.sqrt(2) + 0j      # data REs
+    for l in range(num_layers):
+        x[:, 0, l][:, mask[0, l]] = pilots[0, l]
+    y = np.einsum("bratl,btlsf->brasf", chan, x)
+    if no is not None:
+        y = y + np.sqrt(no / 2) * (rng.standard_normal(y.shape) + 1j * rng.standard_normal(y.shape))
+    n_sym = len(pc.dmrs_symbol_indices)
+    h, e = OO.ls_estimate(y, mask, pilots, 0.0 if no is None else no)
+    h, e = ON.pusch_ls_combine(h, e, n_sym, length, groups)
+    h_hat, e_hat = OO.nn_interp(h, mask, pilots), OO.nn_interp(e, mask, pilots)
+    want = np.broadcast_to(chan[..., None, None], h_hat.shape)
+    return want, h_hat, e_hat
+
+
+def test_pusch_estimator_sweep_block_constant_channel():
+    """Noiseless: exact recovery for every DMRS configuration of the reference's sweep; AWGN: the empirical error
+    variance equals the predicted one (test_channel_estimation.py:56-62, atol 1e-2)."""
+    rng = np.random.default_rng(12)
+    count = 0
+    for num_layers in (1, 2, 4):
+        for length in (1, 2):
+            for additional_position in range(0, (3 if length == 1 else 1) + 1):
+                for config_type in (1, 2):
+                    for groups in range(1 if num_layers < 4 else 2, (2 if config_type == 1 else 3) + 1):
+                        want, h_hat, _ = _pusch_estimation_case(num_layers, length, additional_position, config_type,
+                                                                groups, rng)
+                        assert np.allclose(want, h_hat, atol=1e-6), (num_layers, length, additional_position, config_type, groups)
+                        count += 1
+    assert count == 78
+    for cfg in ((1, 1, 0, 1, 2), (2, 2, 1, 2, 3), (4, 1, 2, 1, 2)):
+        want, h_hat, e_hat = _pusch_estimation_case(*cfg, rng, no=0.01)
+        assert abs(np.var(want - h_hat) - e_hat.mean()) < 1e-2 and abs(np.var(want - h_hat) / e_hat.mean() - 1) < 0.2
