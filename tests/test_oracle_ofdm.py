@@ -4,6 +4,7 @@ CP correctness and mod->demod round trip for every cp in [0, 72] at fft_size 72 
 linear in frequency / time exactly, LMMSE: noiseless recovery and the statistical identity err_var == mean(no_eff)
 of test/unit/mimo/test_mimo_equalizers.py:55-102 (reduced sample count)."""
 import numpy as np
+import pytest
 
 from oracle import ofdm as F
 
@@ -112,3 +113,48 @@ def test_oracle_channel_generation_restatements():
         for r in range(3):
             want = sum(np.convolve(x[bb, t], taps[bb, r, t]) for t in range(2))
             assert np.allclose(y[bb, r], want)
+
+
+def _interp1_with_linear_extrapolation(xq, xs, ys):
+    """Independent 1-D recipe: np.interp inside [xs[0], xs[-1]], straight-line continuation of the first / last segment
+    outside; a single support point gives a constant (what the reference's in-test recipe does, test_ofdm_channel_
+    estimation.py:17-84)."""
+    xs, ys = np.asarray(xs, float), np.asarray(ys)
+    if len(xs) == 1:
+        return np.full(len(xq), ys[0])
+    out = np.interp(xq, xs, ys.real) + 1j * np.interp(xq, xs, ys.imag)
+    lo, hi = xq < xs[0], xq > xs[-1]
+    out[lo] = ys[0] + (xq[lo] - xs[0]) * (ys[1] - ys[0]) / (xs[1] - xs[0])
+    out[hi] = ys[-1] + (xq[hi] - xs[-1]) * (ys[-1] - ys[-2]) / (xs[-1] - xs[-2])
+    return out
+
+
+@pytest.mark.parametrize("pilot_syms", [[2], [2, 11], [0, 5, 13], [3, 4, 9, 10]])
+@pytest.mark.parametrize("time_avg", [False, True])
+def test_linear_interpolator_random_channels_vs_independent_recipe(pilot_syms, time_avg):
+    """oracle.ofdm.lin_interp on RANDOM pilot values (where a wrong bracketing rule shows) for comb pilot patterns of two
+    transmitters with zero pilots on each other's combs, against np.interp + explicit edge extrapolation."""
+    rng = np.random.default_rng(len(pilot_syms) + 10 * time_avg)
+    s_, f_ = 14, 20
+    mask = F.kronecker_mask(2, 1, s_, f_, pilot_syms)
+    npil = len(pilot_syms) * f_
+    pil = np.zeros((2, 1, len(pilot_syms), f_), complex)
+    pil[0, 0, :, 0::3] = 1.0                                   # tx 0 sounds subcarriers 0, 3, 6, ...
+    pil[1, 0, :, 1::4] = -1j                                   # tx 1 sounds 1, 5, 9, ...
+    pil = pil.reshape(2, 1, npil)
+    hp = (rng.standard_normal((2, 2, 1, npil)) + 1j * rng.standard_normal((2, 2, 1, npil))) * (np.abs(pil) > 0)
+    out = F.lin_interp(hp, mask, pil, time_avg=time_avg)
+    fq, sq = np.arange(f_, dtype=float), np.arange(s_, dtype=float)
+    for b in range(2):
+        for tx in range(2):
+            rows = {}
+            for k, sym in enumerate(pilot_syms):
+                vals = hp[b, tx, 0, k * f_:(k + 1) * f_]
+                sup = np.nonzero(np.abs(pil[tx, 0, k * f_:(k + 1) * f_]) > 0)[0]
+                rows[sym] = _interp1_with_linear_extrapolation(fq, sup, vals[sup])
+            if time_avg:
+                avg = sum(rows.values()) / len(rows)
+                rows = {sym: avg for sym in rows}
+            want = np.stack([_interp1_with_linear_extrapolation(sq, sorted(rows), np.array([rows[s][c] for s in sorted(rows)]))
+                             for c in range(f_)], axis=1)
+            assert np.allclose(out[b, tx, 0], want, atol=1e-12), (b, tx)
