@@ -198,3 +198,46 @@ def test_separable_constellation_detection():
     pts = M.qam(4).copy()
     pts[5] += 0.01
     assert M.separable_levels(pts) is None                                   # perturbed (e.g. trained) constellation
+
+
+def test_pilot_pattern_and_resource_grid_host_checks():
+    """Host containers mirror the reference's own property tests (test/unit/ofdm/test_pilot_pattern.py:11-95):
+    argument validation, pilot / data symbol counts, normalisation, the empty pattern; plus the RE-type bookkeeping of
+    ResourceGrid with guards, DC null and a Kronecker pattern."""
+    from sionna_b200.phy.ofdm import PilotPattern, EmptyPilotPattern, KroneckerPilotPattern, ResourceGrid
+    with pytest.raises(AssertionError):
+        PilotPattern(np.zeros([1, 10], bool), np.zeros([1, 10, 20], np.complex64))               # mask rank
+    with pytest.raises(AssertionError):
+        PilotPattern(np.zeros([4, 2, 10, 46], bool), np.zeros([1, 10, 20, 2], np.complex64))      # pilots rank
+    mask = np.zeros([1, 2, 14, 64], bool)
+    mask[0, 0, 0, :] = True
+    mask[0, 1, 1, :] = True
+    with pytest.raises(AssertionError):
+        PilotPattern(mask, np.zeros([1, 3, 64], np.complex64))                                     # leading dims differ
+    with pytest.raises(AssertionError):
+        PilotPattern(mask, np.zeros([1, 2, 65], np.complex64))                                     # wrong pilot count
+    bad = mask.copy()
+    bad[0, 1, 1:3, :] = True
+    with pytest.raises(AssertionError):
+        PilotPattern(bad, np.zeros([1, 2, 128], np.complex64))                                     # unequal counts
+    pp = PilotPattern(mask, np.zeros([1, 2, 64], np.complex64))
+    assert (pp.num_pilot_symbols, pp.num_data_symbols) == (64, 13 * 64)
+    m2 = np.zeros([1, 2, 14, 64], bool)
+    m2[0, 0, :2, :] = True
+    m2[0, 1, 1:3, :] = True
+    pp2 = PilotPattern(m2, np.zeros([1, 2, 128], np.complex64))
+    assert (pp2.num_pilot_symbols, pp2.num_data_symbols) == (128, 12 * 64)
+    ppn = PilotPattern(mask, 3 * np.ones([1, 2, 64], np.complex64), normalize=True)
+    assert np.allclose(np.mean(np.abs(ppn.pilots) ** 2, -1), 1.0)
+    e = EmptyPilotPattern(4, 2, 14, 55)
+    assert (e.num_pilot_symbols, e.num_data_symbols) == (0, 14 * 55)
+    rg = ResourceGrid(14, 76, 15e3, num_tx=2, num_streams_per_tx=2, cyclic_prefix_length=6, num_guard_carriers=(5, 6),
+                      dc_null=True, pilot_pattern="kronecker", pilot_ofdm_symbol_indices=[2, 11])
+    assert rg.num_effective_subcarriers == 64 and rg.num_pilot_symbols == 2 * 64 and rg.num_data_symbols == 12 * 64
+    assert rg.num_resource_elements == 14 * 76 and rg.num_time_samples == 14 * 82 and rg.bandwidth == 76 * 15e3
+    kp = rg.pilot_pattern
+    assert isinstance(kp, KroneckerPilotPattern) and kp.mask.shape == (2, 2, 14, 64)
+    nz = np.abs(kp.pilots.reshape(4, 2, 64)) > 0
+    assert np.all(nz.sum(axis=0) == 1)                      # the four streams sound disjoint subcarrier combs
+    assert np.allclose(np.mean(np.abs(kp.pilots) ** 2, -1), 1.0)
+    assert rg.dc_ind == 38 and 38 not in rg.effective_subcarrier_ind and len(rg.effective_subcarrier_ind) == 64
