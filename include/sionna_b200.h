@@ -72,6 +72,18 @@ int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, in
                          const int32_t* h_in_map, int32_t n_in,
                          const int32_t* h_out_vn, int32_t n_out,
                          const int32_t* h_schedule, int32_t n_sub, int32_t n_active);
+/* Same, but every per-node reduction runs in the REFERENCE's list order instead of ascending neighbour index:
+ *   h_cn_view [num_edges]: `v2c_perm = np.argsort(cn_idx)` (decoding.py:329) - position j of the CN view holds edge
+ *   h_cn_view[j]; a CN combines its edges in that order, a VN sums its edges in ascending edge number (the argsort
+ *   order of decoding.py:286-288). fp32 sums depend on their order, and below the decoding threshold BP amplifies a
+ *   last-bit difference into different hard decisions, so bit-exact agreement with the reference's arithmetic needs
+ *   this order. Such graphs always run the generic kernel (sb_ldpc_graph_set_qc refuses them). */
+int sb_ldpc_graph_create_ordered(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, int32_t num_edges,
+                                 const int32_t* h_cn_of_edge, const int32_t* h_vn_of_edge,
+                                 const int32_t* h_in_map, int32_t n_in,
+                                 const int32_t* h_out_vn, int32_t n_out,
+                                 const int32_t* h_schedule, int32_t n_sub, int32_t n_active,
+                                 const int32_t* h_cn_view);
 void sb_ldpc_graph_destroy(sb_ldpc_graph* g);
 /* Optional: declare the graph quasi-cyclic (lifted base graph, fec/ldpc/encoding.py:322-352): n_entries base entries
  * (h_base_row, h_base_col, h_shift) with lifting size Z, meaning CN r*Z+i is connected to VN c*Z+(i+s) mod Z. Entries

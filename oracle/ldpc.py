@@ -19,24 +19,39 @@ from . import build as _build
 CN_RULES = {"boxplus-phi": 0, "boxplus": 1, "minsum": 2, "min": 2, "offset-minsum": 3, "identity": 4}
 VN_RULES = {"sum": 0, "identity": 1}
 _lib = None
+_lib_pure = None
+
+
+def _decl(h):
+    h.sbo_bp_decode.restype = C.c_int
+    h.sbo_bp_decode.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_int]
+    h.sbo_cn_update.restype = None
+    h.sbo_cn_update.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+    h.sbo_vn_update.restype = C.c_float
+    h.sbo_vn_update.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float]
+    h.sbo_phi.restype = C.c_float
+    h.sbo_phi.argtypes = [C.c_float, C.c_int]
+    h.sbo_is_pure_libm.restype = C.c_int
+    return h
 
 
 def lib():
     global _lib
     if _lib is None:
-        h = C.CDLL(_build.build())
-        h.sbo_bp_decode.restype = C.c_int
-        h.sbo_bp_decode.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_int,
-                                    C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int, C.c_int]
-        h.sbo_cn_update.restype = None
-        h.sbo_cn_update.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
-        h.sbo_vn_update.restype = C.c_float
-        h.sbo_vn_update.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float]
-        h.sbo_phi.restype = C.c_float
-        h.sbo_phi.argtypes = [C.c_float, C.c_int]
-        _lib = h
+        _lib = _decl(C.CDLL(_build.build()))
     return _lib
+
+
+def lib_pure():
+    """ldpc_bp_ref.c compiled WITHOUT the product's sb_math.h (libm only; math_mode must be 0)."""
+    global _lib_pure
+    if _lib_pure is None:
+        _build.build()
+        _lib_pure = _decl(C.CDLL(_build.OUT_LIBM))
+        assert _lib_pure.sbo_is_pure_libm() == 1
+    return _lib_pure
 
 
 def _p(a):
@@ -75,7 +90,7 @@ def ref_edges(pcm):
 
 def bp_decode(pcm, llr_ch, num_iter=20, cn_update="boxplus-phi", vn_update="sum", llr_max=20.0, hard_out=True,
               msg_v2c=None, return_state=False, cn_schedule=None, offset=0.5, math_mode=0, order="reference",
-              num_threads=None, edges=None):
+              num_threads=None, edges=None, pure=False):
     """LDPCBPDecoder.call on ``llr_ch [B, N]`` (logits). ``msg_v2c``/returned state are ``[E, B]`` in the
     reference's edge order. ``order``: "reference" sums node inputs in the reference's own list orders
     (argsort results, decoding.py:286, 329); "kernel" in ascending neighbour index, the CUDA kernels' order."""
@@ -110,7 +125,7 @@ def bp_decode(pcm, llr_ch, num_iter=20, cn_update="boxplus-phi", vn_update="sum"
     x = np.empty((B_, N_), np.float32)
     if num_threads is None:
         num_threads = os.cpu_count() or 1
-    rc = lib().sbo_bp_decode(C_, N_, E_, _p(vn_ptr), _p(cn_ptr), _p(cn_edge), _p(sched), sched.shape[0],
+    rc = (lib_pure() if pure else lib()).sbo_bp_decode(C_, N_, E_, _p(vn_ptr), _p(cn_ptr), _p(cn_edge), _p(sched), sched.shape[0],
                              sched.shape[1], flooding, _p(llr_ch), B_, int(num_iter), CN_RULES[cn_update],
                              VN_RULES[vn_update], float(offset), float(llr_max), int(hard_out), _p(st_in),
                              _p(st_out), _p(x), int(math_mode), int(num_threads))
@@ -283,7 +298,8 @@ class LDPC5GDecoderRef:
             self.schedule = np.asarray(cn_schedule)
         self.edges = ref_edges(self.pcm)
 
-    def __call__(self, llr_ch, num_iter=None, msg_v2c=None, math_mode=0, order="reference", num_threads=None):
+    def __call__(self, llr_ch, num_iter=None, msg_v2c=None, math_mode=0, order="reference", num_threads=None,
+                 pure=False):
         enc = self.enc
         llr_ch = np.asarray(llr_ch, np.float32)
         shape = list(llr_ch.shape)
@@ -304,7 +320,7 @@ class LDPC5GDecoderRef:
                         cn_update=self.cn_update, vn_update=self.vn_update, llr_max=self.llr_max,
                         hard_out=self.hard_out, msg_v2c=msg_v2c, return_state=self.return_state,
                         cn_schedule=self.schedule, math_mode=math_mode, order=order, num_threads=num_threads,
-                        edges=self.edges)
+                        edges=self.edges, pure=pure)
         x_hat, st = out if self.return_state else (out, None)
         if self.return_infobits:                                                             # :1486-1499
             res = x_hat[:, :enc.k].reshape(shape[:-1] + [enc.k])

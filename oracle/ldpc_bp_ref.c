@@ -34,7 +34,18 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+/* -DSBO_PURE_LIBM builds oracle/_build/libsbo_libm.so: this file WITHOUT the product's sb_math.h (math_mode 1 is then
+ * refused), i.e. an oracle that shares no line of code with sionna_b200/. The order="reference" parity tests of the
+ * rules without transcendental functions (minsum, offset-minsum) and the libm-mode comparisons run against it. */
+#ifndef SBO_PURE_LIBM
 #include "../sionna_b200/csrc/sb_math.h"
+#else
+static inline float sb_expf(float x) { (void)x; return NAN; }
+static inline float sb_logf(float x) { (void)x; return NAN; }
+static inline float sb_logf_tab(float x) { (void)x; return NAN; }
+static inline float sb_tanhf(float x) { (void)x; return NAN; }
+static inline float sb_atanhf(float x) { (void)x; return NAN; }
+#endif
 
 enum { SBO_CN_PHI = 0, SBO_CN_TANH = 1, SBO_CN_MINSUM = 2, SBO_CN_OFFSET_MINSUM = 3, SBO_CN_IDENTITY = 4 };
 enum { SBO_VN_SUM = 0, SBO_VN_IDENTITY = 1 };
@@ -166,6 +177,13 @@ float sbo_vn_update(int rule, const float* c2v, float* out, int deg, float llr_c
 }
 
 float sbo_phi(float x, int math_mode) { return phi(x, math_mode); }
+int sbo_is_pure_libm(void) {
+#ifdef SBO_PURE_LIBM
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 /* Full decoder, decoding.py:544-637.
  *  llr_ch   [B, N]  logits as passed to LDPCBPDecoder.call
@@ -181,6 +199,9 @@ int sbo_bp_decode(int C, int N, int E,
                   int cn_rule, int vn_rule, float offset, float llr_max,
                   int hard_out, const float* state_in, float* state_out, float* x_out,
                   int math_mode, int num_threads) {
+#ifdef SBO_PURE_LIBM
+    if (math_mode != 0) return -1;
+#endif
     int max_deg = 0;
     for (int c = 0; c < C; ++c) if (cn_ptr[c + 1] - cn_ptr[c] > max_deg) max_deg = cn_ptr[c + 1] - cn_ptr[c];
     for (int v = 0; v < N; ++v) if (vn_ptr[v + 1] - vn_ptr[v] > max_deg) max_deg = vn_ptr[v + 1] - vn_ptr[v];

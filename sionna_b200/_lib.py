@@ -22,6 +22,7 @@ SIGNATURES = {
     "sb_version": (i32, []),
     "sb_launch_count": (i64, []),
     "sb_ldpc_graph_create": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32]),
+    "sb_ldpc_graph_create_ordered": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp]),
     "sb_ldpc_graph_destroy": (None, [vp]),
     "sb_ldpc_graph_set_qc": (i32, [vp, i32, i32, vp, vp, vp]),
     "sb_ldpc_graph_is_qc": (i32, [vp]),

@@ -345,10 +345,13 @@ static size_t bp_smem_bytes(const sb_ldpc_graph* g, bool smem_msgs) {
     return floats * 4 + ints * 4 + 16 + 16;
 }
 
-extern "C" int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, int32_t num_edges,
-                                    const int32_t* h_cn, const int32_t* h_vn, const int32_t* h_in_map, int32_t n_in,
-                                    const int32_t* h_out_vn, int32_t n_out, const int32_t* h_sched, int32_t n_sub,
-                                    int32_t n_active) {
+// h_cn_view (optional, [E]): the reference's CN-view permutation v2c_perm = np.argsort(cn_idx) (decoding.py:329): the
+// edges of a CN are then walked in that order and the edges of a VN in ascending edge number (the reference's VN order,
+// decoding.py:286-288) instead of ascending neighbour index, so that every sequential sum runs in the reference's order.
+static int graph_create_impl(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, int32_t num_edges,
+                             const int32_t* h_cn, const int32_t* h_vn, const int32_t* h_in_map, int32_t n_in,
+                             const int32_t* h_out_vn, int32_t n_out, const int32_t* h_sched, int32_t n_sub,
+                             int32_t n_active, const int32_t* h_cn_view) {
     SB_CHECK_ARG(out && num_cn > 0 && num_vn > 0 && num_edges >= 0 && (num_edges == 0 || (h_cn && h_vn)),
                  "sb_ldpc_graph_create: bad sizes/pointers");
     auto* g = new sb_ldpc_graph();
@@ -380,23 +383,38 @@ extern "C" int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t
     g->cn_off.assign(g->Lc + 1, 0); g->vn_off.assign(g->Lv + 1, 0);
     for (int l = 0; l < g->Lc; ++l) g->cn_off[l + 1] = g->cn_off[l] + g->cn_cnt[l];
     for (int l = 0; l < g->Lv; ++l) g->vn_off[l + 1] = g->vn_off[l] + g->vn_cnt[l];
-    // per-CN edge lists, ascending VN
+    // per-CN edge lists: ascending VN, or (reference order) the position in the caller's CN view
     std::vector<std::vector<std::pair<int, int>>> cl(C), vl(N);
-    for (int e = 0; e < E; ++e) cl[h_cn[e]].push_back({h_vn[e], e});
+    g->ref_order = h_cn_view != nullptr;
+    if (h_cn_view) {
+        std::vector<char> seen(E, 0);
+        for (int j = 0; j < E; ++j) {
+            int e = h_cn_view[j];
+            if (e < 0 || e >= E || seen[e]) { delete g; sb_set_error("sb_ldpc_graph_create_ordered: cn_view is not a permutation"); return SB_EINVAL; }
+            seen[e] = 1;
+            cl[h_cn[e]].push_back({j, e});
+        }
+    } else {
+        for (int e = 0; e < E; ++e) cl[h_cn[e]].push_back({h_vn[e], e});
+    }
     g->slot_of_edge.assign(E, 0);
-    for (int c = 0; c < C; ++c) {
-        std::sort(cl[c].begin(), cl[c].end());
-        for (size_t l = 0; l < cl[c].size(); ++l) {
-            if (l > 0 && cl[c][l].first == cl[c][l - 1].first) {
+    {
+        std::vector<long long> keys(E);
+        for (int e = 0; e < E; ++e) keys[e] = ((long long)h_cn[e] << 32) | (unsigned)h_vn[e];
+        std::sort(keys.begin(), keys.end());
+        for (int e = 1; e < E; ++e)
+            if (keys[e] == keys[e - 1]) {
                 delete g;
-                sb_set_error("sb_ldpc_graph_create: duplicate edge (cn %d, vn %d)", c, cl[c][l].first);
+                sb_set_error("sb_ldpc_graph_create: duplicate edge (cn %d, vn %d)", (int)(keys[e] >> 32), (int)(keys[e] & 0xffffffff));
                 return SB_EINVAL;
             }
-            g->slot_of_edge[cl[c][l].second] = g->cn_off[l] + crank[c];
-        }
     }
-    // per-VN slot lists, ascending CN
-    for (int e = 0; e < E; ++e) vl[h_vn[e]].push_back({h_cn[e], g->slot_of_edge[e]});
+    for (int c = 0; c < C; ++c) {
+        std::sort(cl[c].begin(), cl[c].end());
+        for (size_t l = 0; l < cl[c].size(); ++l) g->slot_of_edge[cl[c][l].second] = g->cn_off[l] + crank[c];
+    }
+    // per-VN slot lists: ascending CN, or (reference order) ascending edge number
+    for (int e = 0; e < E; ++e) vl[h_vn[e]].push_back({h_cn_view ? e : h_cn[e], g->slot_of_edge[e]});
     g->vn_slot.assign(E, 0);
     for (int v = 0; v < N; ++v) {
         std::sort(vl[v].begin(), vl[v].end());
@@ -437,6 +455,23 @@ extern "C" int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t
     }
     *out = g;
     return SB_OK;
+}
+
+extern "C" int sb_ldpc_graph_create(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, int32_t num_edges,
+                                    const int32_t* h_cn, const int32_t* h_vn, const int32_t* h_in_map, int32_t n_in,
+                                    const int32_t* h_out_vn, int32_t n_out, const int32_t* h_sched, int32_t n_sub,
+                                    int32_t n_active) {
+    return graph_create_impl(out, num_cn, num_vn, num_edges, h_cn, h_vn, h_in_map, n_in, h_out_vn, n_out, h_sched, n_sub,
+                             n_active, nullptr);
+}
+
+extern "C" int sb_ldpc_graph_create_ordered(sb_ldpc_graph** out, int32_t num_cn, int32_t num_vn, int32_t num_edges,
+                                            const int32_t* h_cn, const int32_t* h_vn, const int32_t* h_in_map,
+                                            int32_t n_in, const int32_t* h_out_vn, int32_t n_out, const int32_t* h_sched,
+                                            int32_t n_sub, int32_t n_active, const int32_t* h_cn_view) {
+    SB_CHECK_ARG(h_cn_view || num_edges == 0, "sb_ldpc_graph_create_ordered: null cn_view");
+    return graph_create_impl(out, num_cn, num_vn, num_edges, h_cn, h_vn, h_in_map, n_in, h_out_vn, n_out, h_sched, n_sub,
+                             n_active, h_cn_view);
 }
 
 static void free_device(sb_ldpc_graph* g) {

@@ -618,6 +618,8 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
                                     const int32_t* base_col, const int32_t* shift) {
     SB_CHECK_ARG(g && Z > 0 && Z <= 16383 && n_entries > 0 && base_row && base_col && shift, "sb_ldpc_graph_set_qc: bad arguments");
     SB_CHECK_ARG((int)g->h_cn.size() == g->E, "sb_ldpc_graph_set_qc: handle holds no edge list");
+    SB_CHECK_ARG(!g->ref_order, "sb_ldpc_graph_set_qc: the QC kernel sums in ascending neighbour order; graphs created with "
+                                "sb_ldpc_graph_create_ordered stay on the generic kernel");
     const int C = g->C, N = g->N, E = g->E;
     const int n_rows = (C + Z - 1) / Z, n_cols = (N + Z - 1) / Z;
     auto zrow = [&](int r) { return std::min(Z, C - r * Z); };

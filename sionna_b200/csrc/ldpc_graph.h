@@ -8,6 +8,7 @@
 struct sb_ldpc_graph {
     int C = 0, N = 0, E = 0, Lc = 0, Lv = 0, n_in = 0, n_out = 0, n_sub = 1, n_active = 0;
     bool flooding = true;
+    bool ref_order = false;   // node sums follow the reference's list orders (sb_ldpc_graph_create_ordered)
     std::vector<int> cn_off, cn_cnt, vn_off, vn_cnt, in_idx, out_pos, slot_of_edge, sched, cn_order, vn_order;
     std::vector<uint32_t> vn_slot;
     std::vector<int> h_cn, h_vn;   // the caller's edge list (reference VN order), kept for sb_ldpc_graph_set_qc

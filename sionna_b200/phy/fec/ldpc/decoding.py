@@ -30,7 +30,8 @@ def _i32(a):
 class _GraphHandle:
     """Owns one ``sb_ldpc_graph`` (host plan + lazily uploaded device tables)."""
 
-    def __init__(self, num_cn, num_vn, cn_idx, vn_idx, in_map=None, n_in=0, out_vn=None, n_out=0, schedule=None):
+    def __init__(self, num_cn, num_vn, cn_idx, vn_idx, in_map=None, n_in=0, out_vn=None, n_out=0, schedule=None,
+                 cn_view=None):
         self._h = C.c_void_p()
         cn_idx, vn_idx = _i32(cn_idx), _i32(vn_idx)
         in_map = None if in_map is None else _i32(in_map)
@@ -39,9 +40,16 @@ class _GraphHandle:
         if schedule is not None:
             schedule = _i32(schedule)
             n_sub, n_active = schedule.shape
-        check(lib().sb_ldpc_graph_create(C.byref(self._h), num_cn, num_vn, len(vn_idx), ptr(cn_idx), ptr(vn_idx),
-                                         ptr(in_map), int(n_in), ptr(out_vn), int(n_out), ptr(schedule),
-                                         int(n_sub), int(n_active)), "sb_ldpc_graph_create")
+        if cn_view is None:
+            check(lib().sb_ldpc_graph_create(C.byref(self._h), num_cn, num_vn, len(vn_idx), ptr(cn_idx), ptr(vn_idx),
+                                             ptr(in_map), int(n_in), ptr(out_vn), int(n_out), ptr(schedule),
+                                             int(n_sub), int(n_active)), "sb_ldpc_graph_create")
+        else:
+            cn_view = _i32(cn_view)
+            check(lib().sb_ldpc_graph_create_ordered(C.byref(self._h), num_cn, num_vn, len(vn_idx), ptr(cn_idx),
+                                                     ptr(vn_idx), ptr(in_map), int(n_in), ptr(out_vn), int(n_out),
+                                                     ptr(schedule), int(n_sub), int(n_active), ptr(cn_view)),
+                  "sb_ldpc_graph_create_ordered")
         self.num_edges = len(vn_idx)
         self.n_in = int(n_in) if in_map is not None else num_vn
         self.n_out = int(n_out) if out_vn is not None else num_vn
@@ -100,6 +108,12 @@ class LDPCBPDecoder(Block):
     the hard-decided codeword (``hard_out``) or soft logits, plus the ``[num_edges, batch]`` VN->CN message
     state when ``return_state`` is set. ``cn_update`` is one of ``"boxplus-phi"`` (default), ``"boxplus"``,
     ``"minsum"`` / ``"min"``, ``"offset-minsum"``, ``"identity"``; ``vn_update`` one of ``"sum"``, ``"identity"``.
+
+    Extension (keyword ``sum_order``, not in the reference): ``"ascending"`` (default) combines the messages of a node
+    in ascending neighbour index, which the quasi-cyclic fast path needs; ``"reference"`` walks them in the reference's
+    own list orders (``np.argsort`` results of decoding.py:286, 329) on the generic kernel. fp32 sums depend on their
+    order; for codewords that do not converge BP amplifies the last-bit difference, so only ``"reference"`` reproduces
+    the reference's arithmetic bit for bit (for the rules without transcendental functions).
     """
 
     def __init__(self, pcm, cn_update="boxplus-phi", vn_update="sum", cn_schedule="flooding", hard_out=True,
@@ -107,6 +121,10 @@ class LDPCBPDecoder(Block):
                  precision=None, **kwargs):
         if "cn_type" in kwargs:
             raise TypeError("'cn_type' is deprecated; use 'cn_update' instead.")
+        sum_order = kwargs.pop("sum_order", "ascending")
+        if sum_order not in ("ascending", "reference"):
+            raise ValueError("sum_order must be 'ascending' or 'reference'.")
+        self._sum_order = sum_order
         super().__init__(precision=precision, **kwargs)
         if not isinstance(hard_out, bool):
             raise TypeError("hard_out must be bool.")
@@ -186,8 +204,9 @@ class LDPCBPDecoder(Block):
         self._offset = 0.5  # default of cn_update_offset_minsum (decoding.py:755)
 
         in_map, n_in, out_vn, n_out = self._io_maps()
+        cn_view = np.argsort(self._cn_idx) if sum_order == "reference" else None     # v2c_perm, decoding.py:329
         self._graph = _GraphHandle(self._num_cns, self._num_vns, self._cn_idx, self._vn_idx, in_map, n_in,
-                                   out_vn, n_out, schedule)
+                                   out_vn, n_out, schedule, cn_view)
 
     def _io_maps(self):
         """Hook for subclasses folding rate matching into the kernel's load/store maps."""
@@ -344,7 +363,7 @@ class LDPC5GDecoder(LDPCBPDecoder):
                          v2c_callbacks=v2c_callbacks, c2v_callbacks=c2v_callbacks, return_state=return_state,
                          precision=precision, **kwargs)
         # the decoding graph is a (possibly truncated) lifted base graph: let the C side use its QC fast path
-        if os.environ.get("SB_LDPC_DISABLE_QC", "0") != "1":
+        if os.environ.get("SB_LDPC_DISABLE_QC", "0") != "1" and self._sum_order == "ascending":
             br, bc = np.nonzero(encoder._bm >= 0)
             self._graph.set_qc(encoder.z, br, bc, encoder._bm[br, bc] % encoder.z)
 

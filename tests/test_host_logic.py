@@ -54,6 +54,31 @@ def _check_plan(dec):
         assert [ex["vn_slot"][ex["vn_off"][l] + vrank[v]] for l in range(len(es))] == [slot[e] for e in es]
 
 
+def test_graph_plan_reference_order():
+    """sum_order="reference": a CN walks its edges in v2c_perm = np.argsort(cn_idx) order, a VN in ascending edge number
+    (the list orders of decoding.py:286, 329); such graphs refuse the QC description."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    enc = LDPC5GEncoder(200, 500)
+    dec = LDPC5GDecoder(enc, sum_order="reference")
+    assert not dec._graph.is_qc()
+    br, bc = np.nonzero(enc._bm >= 0)
+    assert not dec._graph.set_qc(enc.z, br, bc, enc._bm[br, bc] % enc.z)
+    ex = dec._graph.export()
+    cn_idx, vn_idx = dec._cn_idx, dec._vn_idx
+    crank, vrank = np.argsort(ex["cn_order"]), np.argsort(ex["vn_order"])
+    slot = ex["slot_of_edge"]
+    perm = np.argsort(cn_idx)
+    assert sorted(slot) == list(range(len(slot)))
+    for c in np.random.default_rng(0).choice(dec.num_cns, 50, replace=False):
+        es = perm[cn_idx[perm] == c]                             # CN-view order
+        assert [slot[e] for e in es] == [ex["cn_off"][l] + crank[c] for l in range(len(es))]
+    for v in np.random.default_rng(1).choice(dec.num_vns, 50, replace=False):
+        es = np.nonzero(vn_idx == v)[0]                          # ascending edge number
+        assert [ex["vn_slot"][ex["vn_off"][l] + vrank[v]] for l in range(len(es))] == [slot[e] for e in es]
+    with pytest.raises(ValueError):
+        LDPC5GDecoder(enc, sum_order="random")
+
+
 def test_graph_plan_jds_layout():
     from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder, LDPCBPDecoder
     from sionna_b200.phy.fec.utils import load_parity_check_examples

@@ -222,3 +222,67 @@ def test_device_phi_scalar_and_packed_equal_oracle(cuda_device):
     ref = np.array([O.phi(v, 1) for v in x[:5000]], np.float32)
     assert np.array_equal(o1.cpu().numpy()[:5000], ref)
     assert torch.equal(o1, o2)
+
+
+# ---- reference summation order: bit-exact against an oracle that shares NO code with the product -------------------
+@pytest.mark.parametrize("rule", ["minsum", "offset-minsum"])
+@pytest.mark.parametrize("k,n,ebno", [(1024, 2048, 0.5), (4224, 8448, 1.0)])
+def test_reference_order_minsum_bit_exact_vs_pure_libm_oracle(cuda_device, rule, k, n, ebno):
+    """sum_order="reference": every node reduction runs in the reference's own list order (the np.argsort results of
+    decoding.py:286, 329). (offset-)min-sum uses no transcendental function, so the CUDA result must equal the oracle
+    built WITHOUT the product's sb_math.h (oracle/_build/libsbo_libm.so, math_mode 0, order "reference") bit for bit -
+    soft outputs, hard decisions and the msg_v2c state - also BELOW the waterfall where most codewords do not
+    converge and a different summation order changes ~10 % of the hard decisions (VERDICT r01, weak #1)."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    rng = np.random.default_rng(k + 17)
+    enc_r = O.LDPC5GEncoderRef(k, n)
+    u = rng.integers(0, 2, (48, k))
+    llr = _noisy_llr(enc_r(u), ebno, k / n, rng)
+    enc = LDPC5GEncoder(k, n)
+    dec = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20, return_state=True,
+                        sum_order="reference")
+    assert not dec._graph.is_qc()
+    x, st = dec(torch.from_numpy(llr).to(cuda_device))
+    ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20,
+                             return_state=True)
+    xr, sr = ref(llr, math_mode=0, order="reference", pure=True)
+    assert np.array_equal(x.cpu().numpy(), xr)
+    assert np.array_equal(st.cpu().numpy(), sr)
+    # the default (ascending) order differs on these non-converged inputs: the orders are not interchangeable
+    xa = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20)(
+        torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+    assert not np.array_equal(xa, xr)
+    hb = LDPC5GDecoder(enc, cn_update=rule, num_iter=20, sum_order="reference")(torch.from_numpy(llr).to(cuda_device))
+    hr = O.LDPC5GDecoderRef(enc_r, cn_update=rule, num_iter=20)(llr, math_mode=0, order="reference", pure=True)
+    assert np.array_equal(hb.cpu().numpy(), hr)
+
+
+@pytest.mark.parametrize("pcm_id", [2, 3, 4])
+def test_reference_order_generic_pcm(cuda_device, pcm_id):
+    """Same for generic parity-check matrices (BCH(127,106), (3,6)-LDPC, 802.11n), all rules: min-sum vs the pure-libm
+    oracle; the transcendental rules vs the kernel-math oracle in reference order."""
+    from sionna_b200.phy.fec.ldpc import LDPCBPDecoder
+    pcm = _example_pcm(pcm_id)
+    rng = np.random.default_rng(200 + pcm_id)
+    llr = (rng.normal(size=(33, pcm.shape[1])) * 2 + 0.5).astype(np.float32)
+    for rule in RULES:
+        dec = LDPCBPDecoder(pcm, cn_update=rule, hard_out=False, num_iter=12, return_state=True, sum_order="reference")
+        x, st = dec(torch.from_numpy(llr).to(cuda_device))
+        pure = rule in ("minsum", "offset-minsum")
+        xr, sr = O.bp_decode(pcm, llr, num_iter=12, cn_update=rule, hard_out=False, return_state=True,
+                             math_mode=0 if pure else 1, order="reference", pure=pure)
+        assert np.array_equal(x.cpu().numpy(), xr), rule
+        assert np.array_equal(st.cpu().numpy(), sr), rule
+
+
+def test_reference_order_layered(cuda_device):
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    rng = np.random.default_rng(12)
+    k, n = 200, 400
+    enc_r = O.LDPC5GEncoderRef(k, n)
+    llr = _noisy_llr(enc_r(rng.integers(0, 2, (20, k))), 1.0, k / n, rng)
+    dec = LDPC5GDecoder(LDPC5GEncoder(k, n), cn_update="minsum", cn_schedule="layered", hard_out=False, num_iter=6,
+                        sum_order="reference")
+    x = dec(torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+    ref = O.LDPC5GDecoderRef(enc_r, cn_update="minsum", cn_schedule="layered", hard_out=False, num_iter=6)
+    assert np.array_equal(x, ref(llr, math_mode=0, order="reference", pure=True))
