@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// out[b, r, j] = in[b, (in_rows == 1 ? 0 : r), idx[r, j]]  (idx < 0 -> 0).  WORDS = 1 (float) or 2 (complex64).
+// out[b, r, j] = in[b, (in_rows == 1 ? 0 : r), idx[r, j]]  (idx < 0 -> 0).  WORDS = 32-bit words per element: 1 (float),
+// 2 (complex64 / float64) or 4 (complex128) -- a bit copy, so the wider types need no arithmetic variant.
 template <int WORDS>
 __global__ void gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ idx, float* __restrict__ out,
                                    long long B, int R, int J, int in_rows, int L) {
@@ -317,7 +318,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ in, const int* __re
         float* dst = out + row * (long long)J * WORDS;
         for (int j = threadIdx.x; j < J; j += blockDim.x) {
             const int sidx = ip[j];
-            if (WORDS == 2) {
+            if (WORDS == 4) {
+                reinterpret_cast<float4*>(dst)[j] = sidx < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(src)[sidx];
+            } else if (WORDS == 2) {
                 reinterpret_cast<float2*>(dst)[j] = sidx < 0 ? make_float2(0.f, 0.f) : reinterpret_cast<const float2*>(src)[sidx];
             } else {
                 dst[j] = sidx < 0 ? 0.f : src[sidx];
@@ -782,11 +785,13 @@ namespace {
 // Host side of the small-FFT path: stage tables per size, built once and kept on the device.
 struct SmallPlanEntry { SmallFftPlan plan; };
 std::mutex g_small_plan_mutex;
-std::map<int, SmallPlanEntry> g_small_plans;
+std::map<std::pair<int, int>, SmallPlanEntry> g_small_plans;   // (device, fft size): the table lives on that device
 
 int get_small_plan(int n, SmallFftPlan* out) {
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_small_plan_mutex);
-    auto it = g_small_plans.find(n);
+    auto it = g_small_plans.find({dev, n});
     if (it != g_small_plans.end()) { *out = it->second.plan; return SB_OK; }
     FftPlan fp;
     if (make_plan(n, &fp) != 0 || fp.n_radix > 12) { sb_set_error("fft size %d has too many factors", n); return SB_EUNSUPPORTED; }
@@ -812,7 +817,7 @@ int get_small_plan(int n, SmallFftPlan* out) {
     SB_CUDA(cudaMalloc((void**)&d, tab.size() * sizeof(unsigned short)));
     SB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     sp.tab = d;
-    g_small_plans[n] = SmallPlanEntry{sp};
+    g_small_plans[{dev, n}] = SmallPlanEntry{sp};
     *out = sp;
     return SB_OK;
 }
@@ -874,6 +879,15 @@ extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, in
     SB_CHECK_ARG(make_plan(fft_size, &plan) == 0, "sb_ofdm_modulate: fft_size has too many factors");
     int threads = std::min(256, std::max(32, (fft_size / 2 + 31) / 32 * 32));
     size_t smem = sizeof(float2) * 3 * (size_t)fft_size;
+    {
+        int dev = 0, optin = 0;
+        SB_CUDA(cudaGetDevice(&dev));
+        SB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (smem > (size_t)optin) {
+            sb_set_error("sb_ofdm_modulate: fft_size %d needs %zu bytes of shared memory per CTA, the device offers %d", fft_size, smem, optin);
+            return SB_EUNSUPPORTED;
+        }
+    }
     SB_CUDA(cudaFuncSetAttribute(ofdm_mod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long jobs = rows * num_symbols;
     int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 8);
@@ -901,6 +915,15 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
     SB_CHECK_ARG(make_plan(fft_size, &plan) == 0, "sb_ofdm_demodulate: fft_size has too many factors");
     int threads = std::min(256, std::max(32, (fft_size / 2 + 31) / 32 * 32));
     size_t smem = sizeof(float2) * 4 * (size_t)fft_size;
+    {
+        int dev = 0, optin = 0;
+        SB_CUDA(cudaGetDevice(&dev));
+        SB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (smem > (size_t)optin) {
+            sb_set_error("sb_ofdm_demodulate: fft_size %d needs %zu bytes of shared memory per CTA, the device offers %d", fft_size, smem, optin);
+            return SB_EUNSUPPORTED;
+        }
+    }
     SB_CUDA(cudaFuncSetAttribute(ofdm_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long jobs = rows * num_symbols;
     int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 8);
@@ -914,13 +937,15 @@ extern "C" int sb_gather_rows(const float* d_in, const int32_t* d_idx, float* d_
                               int32_t cols_out, int32_t in_rows, int32_t cols_in, int32_t words, void* stream) {
     if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(d_in && d_idx && d_out && batch >= 0 && rows > 0 && cols_out > 0 && cols_in > 0 &&
-                     (in_rows == 1 || in_rows == rows) && (words == 1 || words == 2),
+                     (in_rows == 1 || in_rows == rows) && (words == 1 || words == 2 || words == 4),
                  "sb_gather_rows: bad arguments");
     long long total = batch * rows * (long long)cols_out;
     if (total == 0) return SB_OK;
     const RowLaunch rl = row_launch(batch * rows, cols_out);
     if (words == 1)
         gather_rows_kernel<1><<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
+    else if (words == 4)
+        gather_rows_kernel<4><<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
     else
         gather_rows_kernel<2><<<rl.grid, rl.block, 0, (cudaStream_t)stream>>>(d_in, d_idx, d_out, batch, rows, cols_out, in_rows, cols_in);
     SB_LAUNCH_CHECK();

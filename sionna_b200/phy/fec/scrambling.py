@@ -150,9 +150,15 @@ class Scrambler(Block):
             seq = self._draw([1] + list(xin.shape[1:]), seed, dev)
         else:
             seq = self._draw(list(xin.shape), seed, dev)
-        n = seq.numel()                                         # one row of the kernel = one period of the sequence
+        # kernel rows = leading dimension, so the int32 row length of the C-ABI never sees the whole-tensor size; a
+        # sequence of the full input shape supplies one sequence row per input row, a batch-constant one a single row
+        rows = xin.shape[0] if xin.dim() > 1 else 1
+        n = xin.numel() // max(rows, 1)
+        seq_rows = rows if seq.numel() == xin.numel() else 1
+        if n >= 2 ** 31:
+            raise ValueError("Scrambler: rows of 2^31 or more elements are not supported")
         out = torch.empty_like(xin)
-        check(lib().sb_scramble(ptr(xin), ptr(seq), int(binary), ptr(out), xin.numel() // n, n, 1, current_stream()),
+        check(lib().sb_scramble(ptr(xin), ptr(seq), int(binary), ptr(out), rows, n, seq_rows, current_stream()),
               "sb_scramble")
         return out.to(x.dtype) if x.dtype.is_floating_point else out
 

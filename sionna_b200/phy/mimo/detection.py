@@ -17,11 +17,18 @@ class LinearDetector(Block):
         super().__init__(precision=precision, **kwargs)
         self._output = output
         self._hard_out = hard_out
+        # same argument checks and error types as the reference (detection.py:103-115)
         if isinstance(equalizer, str):
-            assert equalizer in ["lmmse"], "Only the 'lmmse' equalizer is provided (zf / mf are out of scope)."
+            assert equalizer in ["lmmse", "zf", "mf"], "Unknown equalizer."
+            if equalizer != "lmmse":
+                raise NotImplementedError(f"equalizer='{equalizer}': only the LMMSE equaliser has a kernel here "
+                                          "(pass a callable (y, h, s) -> (x_hat, no_eff) for anything else).")
             equalizer = lmmse_equalizer
         self._equalizer = equalizer
-        assert output in ("bit",), "Only output='bit' is provided."
+        assert output in ("bit", "symbol"), "Unknown output"
+        assert demapping_method in ("app", "maxlog"), "Unknown demapping method"
+        if output != "bit":
+            raise NotImplementedError("output='symbol' (SymbolDemapper) is not provided; use output='bit'.")
         self._constellation = Constellation.check_or_create(constellation_type=constellation_type,
                                                             num_bits_per_symbol=num_bits_per_symbol,
                                                             constellation=constellation, precision=precision)

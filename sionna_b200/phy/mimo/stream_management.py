@@ -75,40 +75,36 @@ class StreamManagement:
 
     @rx_tx_association.setter
     def rx_tx_association(self, rx_tx_association):
-        a = np.array(rx_tx_association, np.int32)
-        assert all(x in [0, 1] for x in np.nditer(a)), "All elements of `stream_association` must be 0 or 1"
-        self._num_rx, self._num_tx = np.shape(a)
-        num_tx_per_rx = np.sum(a, 1)
-        assert np.min(num_tx_per_rx) == np.max(num_tx_per_rx), \
-            "Each receiver needs to be associated with the same number of transmitters."
-        self._num_tx_per_rx = num_tx_per_rx[0]
-        num_rx_per_tx = np.sum(a, 0)
-        assert np.min(num_rx_per_tx) == np.max(num_rx_per_tx), \
-            "Each transmitter needs to be associated with the same number of receivers."
-        self._num_rx_per_tx = num_rx_per_tx[0]
-        self._rx_tx_association = a
-        self._precoding_ind = np.zeros([self.num_tx, self.num_rx_per_tx], np.int32)
-        for i in range(self.num_tx):
-            self._precoding_ind[i, :] = np.where(a[:, i])[0]
-        sa = np.zeros([self.num_rx, self.num_tx, self.num_streams_per_tx], np.int32)
-        n_streams = np.min([self.num_streams_per_rx, self.num_streams_per_tx])
-        for j in range(self.num_tx):
-            c = 0
-            for i in range(self.num_rx):
-                if a[i, j]:
-                    sa[i, j, c:c + self.num_streams_per_rx] = np.ones([n_streams])
-                    c += self.num_streams_per_rx
-        self._stream_association = sa
-        self._detection_desired_ind = np.where(np.reshape(sa, [-1]) == 1)[0]
-        self._detection_undesired_ind = np.where(np.reshape(sa, [-1]) == 0)[0]
-        self._tx_stream_ids = np.reshape(np.arange(0, self.num_tx * self.num_streams_per_tx),
-                                         [self.num_tx, self.num_streams_per_tx])
-        self._rx_stream_ids = np.zeros([self.num_rx, self.num_streams_per_rx], np.int32)
-        for i in range(self.num_rx):
-            c = []
-            for j in range(self.num_tx):
-                if a[i, j]:
-                    tmp = np.where(sa[i, j])[0] + j * self.num_streams_per_tx
-                    c += list(tmp)
-            self._rx_stream_ids[i, :] = c
-        self._stream_ind = np.argsort(np.reshape(self._rx_stream_ids, [-1]))
+        """Derives every index array from the association matrix with array operations (the reference builds them
+        with nested loops, stream_management.py:165-246; tests/test_host_logic.py compares all of them with outputs
+        of the reference class stored in tests/golden/stream_management_golden.json)."""
+        assoc = np.array(rx_tx_association, np.int32)
+        if assoc.ndim != 2 or not np.isin(assoc, (0, 1)).all():
+            raise AssertionError("All elements of `stream_association` must be 0 or 1")
+        per_rx, per_tx = assoc.sum(axis=1), assoc.sum(axis=0)
+        if per_rx.min() != per_rx.max():
+            raise AssertionError("Each receiver needs to be associated with the same number of transmitters.")
+        if per_tx.min() != per_tx.max():
+            raise AssertionError("Each transmitter needs to be associated with the same number of receivers.")
+        self._num_rx, self._num_tx = assoc.shape
+        self._num_tx_per_rx, self._num_rx_per_tx = per_rx[0], per_tx[0]
+        self._rx_tx_association = assoc
+        s_tx, s_rx = self.num_streams_per_tx, self.num_streams_per_rx
+        # receivers of every transmitter, ascending: column-major scan of the non-zeros
+        self._precoding_ind = np.nonzero(assoc.T)[1].reshape(self.num_tx, self._num_rx_per_tx).astype(np.int32)
+        # the q-th receiver of a transmitter is served by that transmitter's streams [q*s_rx, (q+1)*s_rx)
+        q = np.cumsum(assoc, axis=0) - 1
+        k = np.arange(s_tx)
+        lo = (q * s_rx)[:, :, None]
+        served = (assoc[:, :, None] == 1) & (k >= lo) & (k < lo + s_rx)
+        if (served.sum(axis=(1, 2)) != s_rx).any():
+            raise ValueError("could not distribute the transmitters' streams: a transmitter needs num_rx_per_tx * "
+                             "num_streams_per_rx streams")
+        self._stream_association = served.astype(np.int32)
+        flat = served.reshape(-1)
+        self._detection_desired_ind = np.flatnonzero(flat)
+        self._detection_undesired_ind = np.flatnonzero(~flat)
+        self._tx_stream_ids = np.arange(self.num_tx * s_tx).reshape(self.num_tx, s_tx)
+        # global stream numbers (tx * s_tx + k) received by each receiver, ascending
+        self._rx_stream_ids = np.nonzero(served.reshape(self.num_rx, -1))[1].reshape(self.num_rx, s_rx).astype(np.int32)
+        self._stream_ind = np.argsort(self._rx_stream_ids.reshape(-1))

@@ -14,8 +14,14 @@ class LinearDetector(Block):
     def __init__(self, equalizer, output, demapping_method, resource_grid, stream_management, constellation_type=None,
                  num_bits_per_symbol=None, constellation=None, hard_out=False, precision=None, **kwargs):
         super().__init__(precision=precision, **kwargs)
-        assert equalizer == "lmmse", "Only the 'lmmse' equalizer is provided (zf / mf are out of scope)."
-        assert output == "bit", "Only output='bit' is provided."
+        # same argument checks and error types as the reference (mimo/detection.py:103-115)
+        assert not isinstance(equalizer, str) or equalizer in ["lmmse", "zf", "mf"], "Unknown equalizer."
+        assert output in ("bit", "symbol"), "Unknown output"
+        assert demapping_method in ("app", "maxlog"), "Unknown demapping method"
+        if equalizer != "lmmse":
+            raise NotImplementedError(f"equalizer={equalizer!r}: only 'lmmse' has a fused OFDM kernel here.")
+        if output != "bit":
+            raise NotImplementedError("output='symbol' (SymbolDemapper) is not provided; use output='bit'.")
         self._constellation = Constellation.check_or_create(constellation_type=constellation_type,
                                                             num_bits_per_symbol=num_bits_per_symbol,
                                                             constellation=constellation, precision=precision)

@@ -9,8 +9,11 @@ from .pilot_pattern import PilotPattern, EmptyPilotPattern, KroneckerPilotPatter
 
 def gather_rows(x, idx_dev, rows, cols_out, in_rows, cols_in):
     """out[b, r, j] = x[b, (0 | r), idx[r, j]] through ``sb_gather_rows``; x is [batch, in_rows, cols_in] (float32 or
-    complex64, contiguous); returns [batch, rows, cols_out]."""
-    words = 2 if x.dtype == torch.complex64 else 1
+    complex64, contiguous; float64 / complex128 are copied bit for bit as 2 / 4 words); returns [batch, rows, cols_out]."""
+    if x.dtype not in (torch.float32, torch.complex64, torch.float64, torch.complex128):
+        raise NotImplementedError(f"gather_rows: unsupported dtype {x.dtype}")
+    words = x.element_size() // 4
+    x = x.contiguous()
     batch = x.numel() // (in_rows * cols_in)
     out = torch.empty((batch, rows, cols_out), dtype=x.dtype, device=x.device)
     check(lib().sb_gather_rows(ptr(x), ptr(idx_dev), ptr(out), batch, rows, cols_out, in_rows, cols_in, words,

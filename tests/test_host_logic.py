@@ -266,3 +266,24 @@ def test_pilot_pattern_and_resource_grid_host_checks():
     assert np.all(nz.sum(axis=0) == 1)                      # the four streams sound disjoint subcarrier combs
     assert np.allclose(np.mean(np.abs(kp.pilots) ** 2, -1), 1.0)
     assert rg.dc_ind == 38 and 38 not in rg.effective_subcarrier_ind and len(rg.effective_subcarrier_ind) == 64
+
+
+def test_stream_management_equals_reference_outputs():
+    """Every derived index array equals what the reference class produced for the same inputs
+    (tests/golden/make_stream_management_golden.py ran /root/reference/src/sionna/phy/mimo/stream_management.py)."""
+    import json
+    import os
+    from sionna_b200.phy.mimo import StreamManagement
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stream_management_golden.json")))
+    assert len(cases) >= 10
+    for c in cases:
+        sm = StreamManagement(np.array(c["rx_tx_association"]), c["num_streams_per_tx"])
+        for f, want in c.items():
+            if f in ("rx_tx_association",):
+                continue
+            got = np.asarray(getattr(sm, f))
+            assert np.array_equal(got, np.asarray(want)), (c["rx_tx_association"], f)
+    with pytest.raises(AssertionError):
+        StreamManagement(np.array([[1, 1], [1, 0]]), 1)
+    with pytest.raises(AssertionError):
+        StreamManagement(np.array([[2]]), 1)
