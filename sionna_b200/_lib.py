@@ -54,6 +54,11 @@ SIGNATURES = {
     "sb_uniform": (i32, [vp, i64, f32, f32, u64, u64, vp]),
     "sb_tdl_sos": (i32, [vp, vp, vp, vp, vp, f32, f32, vp, i64, i32, i32, i32, i32, f32, vp]),
     "sb_cir_to_ofdm": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
+    "sb_phase_table": (i32, [vp, vp, f32, i32, vp, i64, i32, i32, vp]),
+    "sb_cir_gram": (i32, [vp, vp, i64, i32, i32, vp]),
+    "sb_cir_link_scale": (i32, [vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, f32, vp]),
+    "sb_cir_apply": (i32, [vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "sb_spatial_corr": (i32, [vp, vp, vp, i64, i32, i64, vp]),
     "sb_pusch_precode": (i32, [vp, vp, vp, i64, i32, i32, i32, i64, vp]),
     "sb_pusch_ls_combine": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "sb_lmmse_equalize": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),

@@ -31,33 +31,98 @@ def _uniform(shape, lo, hi):
     return out
 
 
-def cir_to_ofdm_channel(frequencies, a, tau, normalize=False):
-    """h_f[b, rx, rx_ant, tx, tx_ant, t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253).
+class _TableCache:
+    """Device copies and phase tables keyed by the identity (+ version counter) of the tensors they were built from;
+    entries keep their sources alive, so an address can never be mistaken for a newer tensor."""
 
-    Delays shared by every link (all TDL models; detected on the tensor): one kernel, ``sb_cir_to_ofdm``, with the
-    [paths, subcarriers] phase table built once. Per-link delays fall back to a batched tensor contraction."""
+    def __init__(self, size=16):
+        self._size, self._items = size, {}
+
+    def get(self, key_tensors, extra, build):
+        key = tuple((id(t), t._version) for t in key_tensors) + tuple(extra)
+        hit = self._items.get(key)
+        if hit is None:
+            if len(self._items) >= self._size:
+                self._items.pop(next(iter(self._items)))
+            hit = (build(), key_tensors)
+            self._items[key] = hit
+        return hit[0]
+
+
+_cache = _TableCache()
+
+
+def _f32_on(t, dev):
+    """float32 contiguous copy of `t` on `dev` (cached per source tensor)."""
+    return _cache.get((t,), ("f32", str(dev)), lambda: t.detach().to(device=dev, dtype=torch.float32).contiguous())
+
+
+def _shared_delays(tau):
+    """True if every link uses the same delays, decided from the tensor's layout only (no device read-back): all
+    leading dimensions are broadcast (stride 0, as `TDL` returns them) or have size 1."""
+    return all(tau.shape[d] == 1 or tau.stride(d) == 0 for d in range(tau.dim() - 1))
+
+
+def _cir_convert(a, tau, x, mode, scale, normalize, denom):
+    """Common body of cir_to_ofdm_channel / cir_to_time_channel: h[..., t, j] = c_link * sum_p a[..., p, t] e[p, j] with
+    e from ``sb_phase_table`` (mode 0: exp(-j 2 pi x_j tau_p); mode 1: sinc(x_j - tau_p * scale)), the per-link
+    normalisation from ``sb_cir_gram`` + ``sb_cir_link_scale`` and the contraction by ``sb_cir_apply``."""
+    if a.dtype != torch.complex64:
+        raise NotImplementedError("CIR conversion kernels are complex64 (precision='single').")
+    if a.dim() != 7:
+        raise ValueError("a must have shape [batch, num_rx, num_rx_ant, num_tx, num_tx_ant, num_paths, num_time_steps]")
     dev = a.device
-    f = frequencies.to(device=dev, dtype=torch.float32)
-    tau = tau.to(dev)
-    shared = tau.numel() > 0 and bool((tau == tau.reshape(-1, tau.shape[-1])[0]).all())
-    if shared and a.dtype == torch.complex64 and a.dim() == 7:
-        b, rx, ra, tx, ta, p, t = a.shape
-        t0 = tau.reshape(-1, tau.shape[-1])[0].to(torch.float32)                       # [paths]
-        ang = -2 * np.pi * t0[:, None].double() * f[None, :].double()
-        e = torch.complex(torch.cos(ang), torch.sin(ang)).to(torch.complex64).contiguous()
-        ac = a.contiguous()
-        h = torch.empty((b, rx, ra, tx, ta, t, f.shape[0]), dtype=torch.complex64, device=dev)
-        check(lib().sb_cir_to_ofdm(ptr(ac), ptr(e), ptr(h), b * rx * ra * tx * ta, p, t, f.shape[0], current_stream()),
-              "sb_cir_to_ofdm")
+    b, rx, ra, tx, ta, p, t = a.shape
+    n_col = x.shape[0]
+    xd = _f32_on(x, dev)
+    shared = _shared_delays(tau)
+    if tau.dim() == 6 and not shared:
+        raise NotImplementedError("per-antenna path delays are not provided (TDL delays are per link)")
+
+    def build_tables(tau_rows, n_tab):
+        e = torch.empty((n_tab, p, n_col), dtype=torch.complex64, device=dev)
+        check(lib().sb_phase_table(ptr(tau_rows), ptr(xd), float(scale), mode, ptr(e), n_tab, p, n_col, current_stream()),
+              "sb_phase_table")
+        g = None
+        if normalize:
+            g = torch.empty((n_tab, p, p), dtype=torch.complex64, device=dev)
+            check(lib().sb_cir_gram(ptr(e), ptr(g), n_tab, p, n_col, current_stream()), "sb_cir_gram")
+        return e, g
+
+    if shared:
+        base = tau._base if tau._base is not None else tau
+
+        def build_shared():
+            t0 = tau.reshape(-1, tau.shape[-1])[:1].to(device=dev, dtype=torch.float32).contiguous()
+            return build_tables(t0, 1)
+        e, g = _cache.get((base, x), (mode, float(scale), bool(normalize), str(dev), p), build_shared)
+        stride_e = stride_g = 0
     else:
-        if tau.dim() == 4:                                    # [b, rx, tx, paths] -> broadcast over antennas
-            tau = tau[:, :, None, :, None, :]
-        e = torch.exp(torch.complex(torch.zeros((), device=dev), -2 * np.pi * tau[..., None] * f))   # [..., paths, F]
-        h = torch.einsum("brmtnpl,brmtnpf->brmtnlf", a, e.expand(*a.shape[:-1], f.shape[0]).to(a.dtype))
+        if tuple(tau.shape) != (b, rx, tx, p):
+            raise ValueError("tau must have shape [batch, num_rx, num_tx, num_paths]")
+        e, g = build_tables(tau.to(device=dev, dtype=torch.float32).contiguous(), b * rx * tx)
+        stride_e, stride_g = p * n_col, p * p
+    ac = a.contiguous()
+    sc = None
     if normalize:
-        c = torch.sqrt(torch.mean(torch.abs(h) ** 2, dim=(2, 4, 5, 6), keepdim=True))
-        h = h / c.to(h.dtype)
+        sc = torch.empty(b * rx * tx, dtype=torch.float32, device=dev)
+        check(lib().sb_cir_link_scale(ptr(ac), ptr(g), stride_g, ptr(sc), b, rx, ra, tx, ta, p, t, float(denom),
+                                      current_stream()), "sb_cir_link_scale")
+    h = torch.empty((b, rx, ra, tx, ta, t, n_col), dtype=torch.complex64, device=dev)
+    check(lib().sb_cir_apply(ptr(ac), ptr(e), stride_e, ptr(sc), ptr(h), b, rx, ra, tx, ta, p, t, n_col,
+                             current_stream()), "sb_cir_apply")
     return h
+
+
+def cir_to_ofdm_channel(frequencies, a, tau, normalize=False):
+    """h_f[b, rx, rx_ant, tx, tx_ant, t, f] = sum_p a[..., p, t] exp(-j 2 pi f tau_p) (channel/utils.py:180-253);
+    ``normalize``: unit average energy per resource element and link (:246-251).
+
+    Three hand-written kernels and no tensor expression: the phase table (built once and cached when all links share
+    their delays, which is decided from the layout of ``tau`` without reading it back; one table per link otherwise),
+    the per-link normalisation factor from the taps and the table's Gram matrix, and the contraction that writes the
+    scaled ``h`` once (csrc/channel.cu)."""
+    return _cir_convert(a, tau, frequencies, 0, 0.0, normalize, float(frequencies.shape[0]))
 
 
 class TDL(Block):
@@ -102,14 +167,20 @@ class TDL(Block):
         self._min_speed = float(min_speed)
         self._max_speed = self._min_speed if max_speed is None else float(max_speed)
         assert self._max_speed >= self._min_speed, "min_speed cannot be larger than max_speed"
-        self._corr = None
+        # spatial correlation: ONE lower-triangular factor over the rx_ant * tx_ant antenna pairs (rx antenna major);
+        # separate rx / tx matrices R, T mean V' = L_r V L_t^H, i.e. vec(V') = kron(L_r, conj(L_t)) vec(V)
+        self._corr_l = None
         if spatial_corr_mat is not None:
             m = torch.as_tensor(np.asarray(spatial_corr_mat), dtype=torch.complex64)
-            self._corr = ("full", torch.linalg.cholesky(m))
+            self._corr_l = torch.linalg.cholesky(m)
         elif rx_corr_mat is not None or tx_corr_mat is not None:
-            r = None if rx_corr_mat is None else torch.linalg.cholesky(torch.as_tensor(np.asarray(rx_corr_mat), dtype=torch.complex64))
-            t = None if tx_corr_mat is None else torch.linalg.cholesky(torch.as_tensor(np.asarray(tx_corr_mat), dtype=torch.complex64))
-            self._corr = ("kron", r, t)
+            def chol(m, size):
+                if m is None:
+                    return torch.eye(size, dtype=torch.complex64)
+                return torch.linalg.cholesky(torch.as_tensor(np.asarray(m), dtype=torch.complex64))
+            self._corr_l = torch.kron(chol(rx_corr_mat, self._num_rx_ant), chol(tx_corr_mat, self._num_tx_ant).conj())
+        self._corr_dev = None
+        self._dev_tau = None
         self._dev_powers = None
 
     def _doppler(self, speed):
@@ -149,6 +220,7 @@ class TDL(Block):
     def delay_spread(self, value):
         if self._scale_delays:
             self._delay_spread = float(value)
+            self._dev_tau = None
         else:
             print("Warning: The delay spread cannot be set with this model")
 
@@ -182,22 +254,18 @@ class TDL(Block):
         if self.precision != "single":
             raise NotImplementedError("TDL generates complex64 taps only.")
         batch_size = int(batch_size)
-        a = self.synthesize(self.draws(batch_size), num_time_steps, sampling_frequency)
+        a = self.synthesize(self.draws(batch_size), num_time_steps, sampling_frequency)   # [B, rx_ant * tx_ant, P, T]
         n, t = self.num_clusters, int(num_time_steps)
+        dev = a.device
+        if self._corr_l is not None:                            # spatial correlation (tdl.py:466-490): v' = L v
+            if self._corr_dev is None or self._corr_dev.device != dev:
+                self._corr_dev = self._corr_l.to(dev).contiguous()
+            out = torch.empty_like(a)
+            check(lib().sb_spatial_corr(ptr(a), ptr(self._corr_dev), ptr(out), batch_size,
+                                        self._num_rx_ant * self._num_tx_ant, n * t, current_stream()), "sb_spatial_corr")
+            a = out
         a = a.reshape(batch_size, 1, self._num_rx_ant, 1, self._num_tx_ant, n, t)
-        if self._corr is not None:                              # spatial correlation: small dense factors (tdl.py:466-490)
-            if self._corr[0] == "full":
-                l = self._corr[1].to(a.device)
-                v = a.permute(0, 1, 3, 5, 6, 2, 4).reshape(batch_size, 1, 1, n, t, -1)
-                v = torch.einsum("ij,...j->...i", l, v).reshape(batch_size, 1, 1, n, t, self._num_rx_ant, self._num_tx_ant)
-                a = v.permute(0, 1, 5, 2, 6, 3, 4).contiguous()
-            else:
-                _, r, tt = self._corr
-                v = a.permute(0, 1, 3, 5, 6, 2, 4)                 # [..., rx_ant, tx_ant]
-                if r is not None:
-                    v = torch.matmul(r.to(a.device), v)
-                if tt is not None:
-                    v = torch.matmul(v, tt.to(a.device).conj().transpose(-1, -2))
-                a = v.permute(0, 1, 5, 2, 6, 3, 4).contiguous()
-        tau = self.delays.to(a.device).reshape(1, 1, 1, n).expand(batch_size, 1, 1, n).contiguous()
-        return a, tau
+        if self._dev_tau is None or self._dev_tau.device != dev:
+            self._dev_tau = self.delays.to(dev).reshape(1, 1, 1, n)
+        # every link has the same delays: a broadcast view (stride 0) says so without any device read-back
+        return a, self._dev_tau.expand(batch_size, 1, 1, n)

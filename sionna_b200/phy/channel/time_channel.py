@@ -19,29 +19,17 @@ def time_lag_discrete_time_channel(bandwidth, maximum_delay_spread=3e-6):
 
 def cir_to_time_channel(bandwidth, a, tau, l_min, l_max, normalize=False):
     """Discrete-time taps hm[b, rx, rx_ant, tx, tx_ant, t, l] = sum_p a[..., p, t] sinc(l - tau_p W), l = l_min..l_max
-    (utils.py:256-350). Delays shared by all links: one `sb_cir_to_ofdm` launch with the real sinc table."""
-    dev = a.device
-    tau = tau.to(dev)
-    l = torch.arange(int(l_min), int(l_max) + 1, dtype=torch.float64, device=dev)
-    shared = tau.numel() > 0 and bool((tau == tau.reshape(-1, tau.shape[-1])[0]).all())
-    if shared and a.dtype == torch.complex64 and a.dim() == 7:
-        b, rx, ra, tx, ta, p, t = a.shape
-        t0 = tau.reshape(-1, tau.shape[-1])[0].double()
-        g = torch.sinc(l[None, :] - t0[:, None] * float(bandwidth))                     # [paths, taps]
-        e = torch.complex(g, torch.zeros_like(g)).to(torch.complex64).contiguous()
-        hm = torch.empty((b, rx, ra, tx, ta, t, l.numel()), dtype=torch.complex64, device=dev)
-        check(lib().sb_cir_to_ofdm(ptr(a.contiguous()), ptr(e), ptr(hm), b * rx * ra * tx * ta, p, t, l.numel(),
-                                   current_stream()), "sb_cir_to_ofdm")
-    else:
-        if tau.dim() == 4:
-            tau = tau[:, :, None, :, None, :].expand(-1, -1, a.shape[2], -1, a.shape[4], -1)
-        g = torch.sinc(l - tau[..., None].double() * float(bandwidth)).to(a.dtype)     # [..., paths, taps]
-        hm = torch.einsum("brmtnpl,brmtnpk->brmtnlk", a, g)
-    if normalize:
-        c = torch.mean(torch.sum(hm.abs() ** 2, dim=6, keepdim=True), dim=(2, 4, 5), keepdim=True)
-        c = torch.sqrt(c)
-        hm = torch.where(c > 0, hm / c.to(hm.dtype), torch.zeros_like(hm))
-    return hm
+    (utils.py:256-350); ``normalize``: unit average total tap energy per link (:341-348). Same three kernels as
+    `cir_to_ofdm_channel` with the real sinc table in place of the phase table."""
+    from .tdl import _cir_convert
+    key = (int(l_min), int(l_max))
+    lags = _LAGS.get(key)
+    if lags is None:
+        lags = _LAGS[key] = torch.arange(int(l_min), int(l_max) + 1, dtype=torch.float32)
+    return _cir_convert(a, tau, lags, 1, float(bandwidth), normalize, 1.0)
+
+
+_LAGS = {}
 
 
 def time_to_ofdm_channel(h_t, rg, l_min):

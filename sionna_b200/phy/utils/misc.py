@@ -6,7 +6,9 @@ full bit tensors (misc.py:540-548, 614-655) by the B200 design of SURVEY.md sect
 (``torchrun``), every rank runs ``mc_fun`` on its own random stream, and after every batch ONE all-reduce (NCCL over
 NVLink; 32 bytes) sums the device-resident int64 counters {bit errors, block errors, bits, blocks}; all ranks
 therefore take identical stopping decisions and ``max_mc_iter`` is divided by the number of replicas exactly as the
-reference does (misc.py:651-655).
+reference does (misc.py:651-655). The host never stalls the GPU for a stopping decision: counters reach pinned host
+memory through asynchronous copies and the next batch is already enqueued when they are read (see the three batch
+modes in ``sim_ber``).
 """
 import time
 import numpy as np
@@ -196,55 +198,158 @@ def sim_ber(mc_fun, ebno_dbs, batch_size, max_mc_iter, soft_estimates=False, num
         print("{: >9} |{: >11} |{: >11} |{: >12} |{: >12} |{: >13} |{: >12} |{: >12} |{: >10}".format(*row_text),
               end=end_str)
 
-    counter = None
+    # ---- batch execution ---------------------------------------------------------------------------------------
+    # The counters of a batch live on the device (sb_count_errors); what differs between the modes is WHEN the host
+    # reads them:
+    #   "sync"  callback given, or mc_fun returns host tensors: read after every batch before anything else happens
+    #           (the callback contract; exactly the reference's sequence of mc_fun calls).
+    #   "lag"   CUDA tensors + a target number of bit / block errors: batch ii+1 is enqueued speculatively BEFORE the
+    #           counters of batch ii are read (asynchronous copy to pinned memory + event), so the GPU never waits for
+    #           the host's stopping decision; when batch ii reaches the target the speculative batch is discarded, i.e.
+    #           the counted batches - and therefore BER/BLER - are those of the reference's rule (misc.py:742-753).
+    #   "free"  CUDA tensors and no per-batch stopping rule: nothing is read until the SNR point is finished (running
+    #           totals are copied asynchronously only to feed the progress line).
+    slots = {}
+
+    def _slots(device):
+        if device not in slots:
+            st = {"dev": [torch.zeros(4, dtype=torch.int64, device=device) for _ in range(2)]}
+            if device.type == "cuda":
+                st["host"] = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(2)]
+                st["ev"] = [torch.cuda.Event() for _ in range(2)]
+                st["run"] = torch.zeros(4, dtype=torch.int64, device=device)
+            slots[device] = st
+        return slots[device]
+
+    def _mc(i):
+        ebno_i = torch.as_tensor(ebno_np[i], dtype=rdtype)
+        outputs = mc_fun(batch_size=batch_size, ebno_db=ebno_i)
+        b, b_hat = outputs[0], outputs[1]
+        if soft_estimates:
+            b_hat = hard_decisions(b_hat)
+        return b, b_hat
+
+    def _post(st, k, src=None):
+        """Reduce slot k over the replicas and start its copy to pinned host memory."""
+        if src is not None:
+            st["dev"][k].copy_(src)
+        if run_multigpu:
+            dist.all_reduce(st["dev"][k], op=dist.ReduceOp.SUM, group=group)
+        st["host"][k].copy_(st["dev"][k], non_blocking=True)
+        st["ev"][k].record()
+
+    def _add(i, c):
+        bit_errors[i] += c[0]
+        block_errors[i] += c[1]
+        nb_bits[i] += c[2]
+        nb_blocks[i] += c[3]
+
+    def _header_once(i, iter_count):
+        if verbose and i == 0 and iter_count == 0:
+            _print_progress(True, 0, 0, 0, header_text)
+            print("-" * 135)
+
+    def _targets_reached(i):
+        if num_target_bit_errors is not None and bit_errors[i] >= num_target_bit_errors:
+            return STATUS_TARGET_BIT
+        if num_target_block_errors is not None and block_errors[i] >= num_target_block_errors:
+            return STATUS_TARGET_BLOCK
+        return None
+
+    per_batch_rule = num_target_bit_errors is not None or num_target_block_errors is not None
     i = 0
     cb_state = sim_ber.CALLBACK_CONTINUE
     try:
         for i in range(num_points):
             runtime[i] = time.perf_counter()
             iter_count = -1
-            for ii in range(max_mc_iter):
-                iter_count += 1
-                ebno_i = torch.as_tensor(ebno_np[i], dtype=rdtype)
-                outputs = mc_fun(batch_size=batch_size, ebno_db=ebno_i)
-                b, b_hat = outputs[0], outputs[1]
-                if soft_estimates:
-                    b_hat = hard_decisions(b_hat)
-                if counter is None or counter.device != b.device:
-                    counter = torch.zeros(4, dtype=torch.int64, device=b.device)
-                counter.zero_()
-                _count_batch(counter, b, b_hat)
-                if run_multigpu:
-                    dist.all_reduce(counter, op=dist.ReduceOp.SUM, group=group)
-                c = counter.cpu().tolist()
-                bit_errors[i] += c[0]
-                block_errors[i] += c[1]
-                nb_bits[i] += c[2]
-                nb_blocks[i] += c[3]
-
-                cb_state = sim_ber.CALLBACK_CONTINUE
-                if callback is not None:
-                    cb_state = callback(ii, i, ebno_np, bit_errors, block_errors, nb_bits, nb_blocks)
-                    if cb_state in (sim_ber.CALLBACK_STOP, sim_ber.CALLBACK_NEXT_SNR):
+            mode = "none"
+            if max_mc_iter >= 1:
+                b, b_hat = _mc(i)                                        # batch 0 of this SNR point
+                st = _slots(b.device)
+                mode = "sync" if (callback is not None or not b.is_cuda) else ("lag" if per_batch_rule else "free")
+            if mode == "free":
+                st["run"].zero_()
+                last = None
+                for ii in range(max_mc_iter):
+                    iter_count = ii
+                    if ii > 0:
+                        b, b_hat = _mc(i)
+                    _count_batch(st["run"], b, b_hat)                    # running totals of this SNR point
+                    k = ii & 1
+                    if verbose and last is not None and st["ev"][last].query():
+                        c = st["host"][last].tolist()                     # newest totals that have already arrived
+                        bit_errors[i], block_errors[i], nb_bits[i], nb_blocks[i] = c
+                    _post(st, k, st["run"])
+                    last = k
+                    _header_once(i, ii)
+                    if verbose:
+                        _print_progress(False, time.perf_counter() - runtime[i], i, ii)
+                st["ev"][last].synchronize()
+                c = st["host"][last].tolist()
+                bit_errors[i], block_errors[i], nb_bits[i], nb_blocks[i] = c
+                runtime[i] = time.perf_counter() - runtime[i]
+                status[i] = STATUS_MAX_IT
+            elif mode == "lag":
+                k = 0
+                st["dev"][k].zero_()
+                _count_batch(st["dev"][k], b, b_hat)
+                _post(st, k)
+                ii = 0
+                while True:
+                    iter_count = ii
+                    speculative = ii + 1 < max_mc_iter
+                    if speculative:                                       # enqueue batch ii+1 before reading batch ii
+                        b, b_hat = _mc(i)
+                        st["dev"][1 - k].zero_()
+                        _count_batch(st["dev"][1 - k], b, b_hat)
+                        _post(st, 1 - k)
+                    st["ev"][k].synchronize()
+                    _add(i, st["host"][k].tolist())
+                    _header_once(i, ii)
+                    if verbose:
+                        _print_progress(False, time.perf_counter() - runtime[i], i, ii)
+                    reached = _targets_reached(i)
+                    if reached is not None:                               # a speculative batch, if any, is not counted
+                        status[i] = reached
                         runtime[i] = time.perf_counter() - runtime[i]
-                        status[i] = STATUS_CB_STOP
                         break
-                if verbose:
-                    if i == 0 and iter_count == 0:
-                        _print_progress(True, 0, 0, 0, header_text)
-                        print("-" * 135)
-                    _print_progress(False, time.perf_counter() - runtime[i], i, ii)
-                if num_target_bit_errors is not None and bit_errors[i] >= num_target_bit_errors:
-                    status[i] = STATUS_TARGET_BIT
-                    runtime[i] = time.perf_counter() - runtime[i]
-                    break
-                if num_target_block_errors is not None and block_errors[i] >= num_target_block_errors:
-                    runtime[i] = time.perf_counter() - runtime[i]
-                    status[i] = STATUS_TARGET_BLOCK
-                    break
-                if iter_count == max_mc_iter - 1:
-                    runtime[i] = time.perf_counter() - runtime[i]
-                    status[i] = STATUS_MAX_IT
+                    if not speculative:
+                        runtime[i] = time.perf_counter() - runtime[i]
+                        status[i] = STATUS_MAX_IT
+                        break
+                    ii += 1
+                    k = 1 - k
+            elif mode == "sync":
+                for ii in range(max_mc_iter):
+                    iter_count = ii
+                    if ii > 0:
+                        b, b_hat = _mc(i)
+                    counter = st["dev"][0]
+                    counter.zero_()
+                    _count_batch(counter, b, b_hat)
+                    if run_multigpu:
+                        dist.all_reduce(counter, op=dist.ReduceOp.SUM, group=group)
+                    _add(i, counter.cpu().tolist())
+
+                    cb_state = sim_ber.CALLBACK_CONTINUE
+                    if callback is not None:
+                        cb_state = callback(ii, i, ebno_np, bit_errors, block_errors, nb_bits, nb_blocks)
+                        if cb_state in (sim_ber.CALLBACK_STOP, sim_ber.CALLBACK_NEXT_SNR):
+                            runtime[i] = time.perf_counter() - runtime[i]
+                            status[i] = STATUS_CB_STOP
+                            break
+                    _header_once(i, ii)
+                    if verbose:
+                        _print_progress(False, time.perf_counter() - runtime[i], i, ii)
+                    reached = _targets_reached(i)
+                    if reached is not None:
+                        status[i] = reached
+                        runtime[i] = time.perf_counter() - runtime[i]
+                        break
+                    if ii == max_mc_iter - 1:
+                        runtime[i] = time.perf_counter() - runtime[i]
+                        status[i] = STATUS_MAX_IT
             if verbose:
                 _print_progress(True, runtime[i], i, iter_count)
             if early_stop:

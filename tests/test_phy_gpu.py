@@ -235,3 +235,41 @@ def test_sim_ber_on_device(cuda_device):
     ber = ber.numpy()
     assert ber[0] > 0.05 and ber[0] > ber[1] > ber[2] and ber[3] < 5e-3
     assert ber[-1] == 0                                      # early stop: remaining points stay 0
+
+
+def test_sim_ber_device_modes_keep_reference_stopping_semantics(cuda_device):
+    """CUDA outputs: counters are read asynchronously ("free": once per SNR point; "lag": one batch late with a speculative
+    next batch). The COUNTED batches must be those of the reference's rules (misc.py:717-760): a target reached by batch
+    ii stops the point with exactly ii+1 batches counted, the speculative batch is discarded."""
+    from sionna_b200.phy.utils import sim_ber
+    calls = []
+
+    def mc_fun(batch_size, ebno_db):
+        calls.append(float(ebno_db))
+        b = torch.zeros(batch_size, 10, device=cuda_device)
+        b_hat = b.clone()
+        if float(ebno_db) < 1.0:
+            b_hat[0, 0] = 1.0                                 # exactly one bit / block error per batch
+        return b, b_hat
+
+    # "lag": 3 batches reach the target (+1 speculative, not counted); 2 dB: 10 error-free batches -> early stop
+    ber, bler = sim_ber(mc_fun, [0.0, 2.0, 4.0], batch_size=5, max_mc_iter=10, num_target_bit_errors=3, verbose=False)
+    assert float(ber[0]) == pytest.approx(3 / (3 * 50)) and float(bler[0]) == pytest.approx(3 / 15)
+    assert float(ber[1]) == 0 and float(ber[2]) == 0
+    assert calls.count(0.0) == 4 and calls.count(2.0) == 10 and calls.count(4.0) == 0
+    # target reached exactly by the last allowed batch: no speculation beyond max_mc_iter
+    calls.clear()
+    ber, _ = sim_ber(mc_fun, [0.0], batch_size=5, max_mc_iter=3, num_target_block_errors=3, verbose=False)
+    assert len(calls) == 3 and float(ber[0]) == pytest.approx(3 / 150)
+    # "free": no per-batch rule -> every batch counted, totals read once per point
+    calls.clear()
+    ber, bler = sim_ber(mc_fun, [0.0, 0.5], batch_size=5, max_mc_iter=7, early_stop=False, verbose=True)
+    assert len(calls) == 14 and float(ber[0]) == pytest.approx(7 / 350) and float(bler[1]) == pytest.approx(7 / 35)
+    # "sync": a callback sees exact per-batch totals
+    seen = []
+
+    def cb(mc_iter, snr_idx, ebnos, bit_errors, block_errors, nb_bits, nb_blocks):
+        seen.append((mc_iter, int(bit_errors[snr_idx]), int(nb_bits[snr_idx])))
+        return sim_ber.CALLBACK_NEXT_SNR if mc_iter == 2 else sim_ber.CALLBACK_CONTINUE
+    sim_ber(mc_fun, [0.0], batch_size=5, max_mc_iter=10, callback=cb, verbose=False)
+    assert seen == [(0, 1, 50), (1, 2, 100), (2, 3, 150)]
