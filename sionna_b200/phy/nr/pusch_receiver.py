@@ -71,7 +71,7 @@ class PUSCHReceiver(Block):
                 h = time_to_ofdm_channel(h, self.resource_grid, self._l_min)
             if self._w is not None:
                 # effective channel per layer: h_eff[b, r, ra, t, l, s, f] = sum_p h[b, r, ra, t, p, s, f] W[t, p, l]
-                h = torch.einsum("bratpsf,tpl->bratlsf", h.to(torch.complex64), self._w.w)
+                h = self._w.effective_channel(h)
             h_hat = h.contiguous()
             err_var = torch.zeros((), dtype=torch.float32, device=h_hat.device)
         else:

@@ -166,3 +166,65 @@ def test_pusch_time_domain_link_over_tdl(cuda_device):
     y2, h_time = chan_h(x, 0.005)
     rx_p = PUSCHReceiver(tx, channel_estimator="perfect", input_domain="time", l_min=l_min)
     assert float((rx_p(y2, 0.005, h_time) != b).float().mean()) < 1e-3
+
+
+def test_cir_normalisation_per_link_delays_and_spatial_correlation(cuda_device):
+    """channel.cu: (1) normalize=True equals the reference recipe h / sqrt(mean |h|^2 over (rx_ant, tx_ant, t, f)) per
+    link computed in float64 from the un-normalised h (channel/utils.py:246-251, :341-348), although the kernel never
+    reads h for it (Gram-matrix form); (2) delays that differ from link to link (tau [batch, rx, tx, paths], not a
+    broadcast view) take the per-link tables; (3) spatial correlation equals L v / R V T^H in NumPy (tdl.py:466-490)."""
+    from sionna_b200.phy.channel import TDL, cir_to_ofdm_channel, cir_to_time_channel, subcarrier_frequencies
+    from sionna_b200.phy.utils import complex_normal
+    from sionna_b200.phy import config
+    from oracle import ofdm as OO
+    config.seed = 41
+    b, rx, ra, tx, ta, p, t, f = 5, 2, 3, 2, 2, 7, 6, 48
+    a = complex_normal([b, rx, ra, tx, ta, p, t])
+    a[1] = 0                                                            # an all-zero link must stay zero (no NaN)
+    freqs = subcarrier_frequencies(f, 30e3)
+    rng = np.random.default_rng(0)
+    tau_link = torch.from_numpy((rng.uniform(0, 2e-6, (b, rx, tx, p))).astype(np.float32))
+    an = a.cpu().numpy().astype(np.complex128)
+    # reference formula with per-link delays
+    e = np.exp(-2j * np.pi * tau_link.numpy().astype(np.float64)[..., None] * freqs.numpy().astype(np.float64))  # [b,rx,tx,p,f]
+    ref = np.einsum("brmtnpl,brtpf->brmtnlf", an, e)
+    h = cir_to_ofdm_channel(freqs, a, tau_link).cpu().numpy()
+    assert np.allclose(h, ref, atol=3e-5)
+    c = np.sqrt(np.mean(np.abs(ref) ** 2, axis=(2, 4, 5, 6), keepdims=True))
+    ref_n = np.where(c > 0, ref / np.where(c > 0, c, 1), 0)
+    hn = cir_to_ofdm_channel(freqs, a, tau_link, normalize=True).cpu().numpy()
+    assert np.all(np.isfinite(hn)) and np.allclose(hn, ref_n, atol=5e-5)
+    # shared delays given as a broadcast view: cached single table, same numbers as the explicit per-link copy
+    tau_shared = tau_link[:1, :1, :1].expand(b, rx, tx, p)
+    h1 = cir_to_ofdm_channel(freqs, a, tau_shared, normalize=True)
+    h2 = cir_to_ofdm_channel(freqs, a, tau_shared.contiguous(), normalize=True)
+    assert torch.allclose(h1, h2, atol=1e-6)
+    # time-domain taps: sinc table, normalisation = unit mean total tap energy per link
+    bw, l_min, l_max = 48 * 30e3, -6, 9
+    hm = cir_to_time_channel(bw, a, tau_link, l_min, l_max).cpu().numpy()
+    l = np.arange(l_min, l_max + 1)
+    g = np.sinc(l - tau_link.numpy().astype(np.float64)[..., None] * bw)                                       # [b,rx,tx,p,L]
+    ref_t = np.einsum("brmtnpl,brtpk->brmtnlk", an, g)
+    assert np.allclose(hm, ref_t, atol=3e-5)
+    ct = np.sqrt(np.mean(np.sum(np.abs(ref_t) ** 2, axis=6, keepdims=True), axis=(2, 4, 5), keepdims=True))
+    ref_tn = np.where(ct > 0, ref_t / np.where(ct > 0, ct, 1), 0)
+    hmn = cir_to_time_channel(bw, a, tau_link, l_min, l_max, normalize=True).cpu().numpy()
+    assert np.allclose(hmn, ref_tn, atol=5e-5)
+    # spatial correlation: identical draws with and without the correlation matrices
+    n_rx, n_tx = 4, 2
+    r_rx = 0.7 ** np.abs(np.subtract.outer(np.arange(n_rx), np.arange(n_rx))) * np.exp(0.3j * np.subtract.outer(np.arange(n_rx), np.arange(n_rx)))
+    r_tx = np.array([[1.0, 0.4 - 0.2j], [0.4 + 0.2j, 1.0]])
+    config.seed = 77
+    a0, _ = TDL("A", 100e-9, 3.5e9, min_speed=5.0, num_rx_ant=n_rx, num_tx_ant=n_tx)(16, 4, 1e3)
+    config.seed = 77
+    a1, _ = TDL("A", 100e-9, 3.5e9, min_speed=5.0, num_rx_ant=n_rx, num_tx_ant=n_tx, rx_corr_mat=r_rx, tx_corr_mat=r_tx)(16, 4, 1e3)
+    lr, lt = np.linalg.cholesky(r_rx), np.linalg.cholesky(r_tx)
+    v = a0.cpu().numpy().astype(np.complex128)[:, 0, :, 0]                 # [B, rx_ant, tx_ant, P, T]
+    want = np.einsum("ij,bjkpt,lk->bilpt", lr, v, lt.conj())
+    assert np.allclose(a1.cpu().numpy()[:, 0, :, 0], want, atol=2e-5)
+    config.seed = 77
+    full = np.kron(r_rx, r_tx)
+    a2, _ = TDL("A", 100e-9, 3.5e9, min_speed=5.0, num_rx_ant=n_rx, num_tx_ant=n_tx, spatial_corr_mat=full)(16, 4, 1e3)
+    lf = np.linalg.cholesky(full)
+    want2 = np.einsum("ij,bjpt->bipt", lf, v.reshape(16, n_rx * n_tx, v.shape[3], v.shape[4])).reshape(v.shape)
+    assert np.allclose(a2.cpu().numpy()[:, 0, :, 0], want2, atol=2e-5)
