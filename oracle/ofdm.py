@@ -191,6 +191,24 @@ def lmmse_equalizer(y, h, s):
     return gy / d, np.real(1 / d - 1)
 
 
+def lmmse_equalizer_f32(y, h, s):
+    """The same formula sequence evaluated in complex64 / float32 (LAPACK single precision), i.e. with the arithmetic
+    precision the reference itself runs at. Not a second oracle: the parity tests use it to MEASURE the reference's own
+    fp32 error envelope against the complex128 evaluation above (how far any single-precision evaluation of
+    mimo/equalization.py:183-233 sits from the exact result), which is the yardstick the CUDA kernel is held to."""
+    y, h, s = y.astype(np.complex64), h.astype(np.complex64), s.astype(np.complex64)
+    l = np.linalg.cholesky(s)
+    l_inv = np.linalg.solve(l, np.broadcast_to(np.eye(s.shape[-1], dtype=np.complex64), s.shape))
+    y_w = (l_inv @ y[..., None])[..., 0]
+    h_w = l_inv @ h
+    a = np.conj(np.swapaxes(h_w, -1, -2)) @ h_w + np.eye(h.shape[-1], dtype=np.complex64)
+    g = np.linalg.solve(a, np.conj(np.swapaxes(h_w, -1, -2)))
+    gy = (g @ y_w[..., None])[..., 0]
+    d = np.diagonal(g @ h_w, axis1=-2, axis2=-1)
+    one = np.float32(1)
+    return (gy / d).astype(np.complex64), np.real(one / d - one).astype(np.float32)
+
+
 def ofdm_lmmse_equalize(y_eff, h_hat, err_var, no, mask, sm):
     """OFDMEqualizer.call + lmmse_equalizer (ofdm/equalization.py:126-275). y_eff [B, rx, ant, S, F] (effective
     subcarriers), h_hat [B, rx, ant, tx, st, S, F] -> x_hat, no_eff [B, tx, st, num_data]."""

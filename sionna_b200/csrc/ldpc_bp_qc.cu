@@ -541,6 +541,9 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
             const bool final_pass = it == p.num_iter - 1;
             const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
+            if (final_pass && tid == 0 && p.use_tma && b + gridDim.x < p.B)   // pull the next codeword's logits into L2 early
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.llr + (size_t)(b + gridDim.x) * p.n_in),
+                             "r"((uint32_t)p.n_in * 4u) : "memory");
             const int* re = p.row_cls_end;
             cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt);
             cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt);
@@ -681,6 +684,41 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
         return row_class(a) != row_class(b) ? row_class(a) < row_class(b) : rdeg[a] > rdeg[b]; });
     std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) {
         return col_class(a) != col_class(b) ? col_class(a) < col_class(b) : cdeg[a] > cdeg[b]; });
+    // Inside a class the order is free. Rows / columns are dealt cyclically to the G warp groups of a launch over ALL
+    // classes (position i -> group i mod G), so the order decides the load balance: walk the positions in rounds of G
+    // consecutive ones (a round gives every group at most one item) and hand the round's heaviest item to the group with
+    // the smallest load so far. Degree order alone left the benchmark graph's four groups with 56/53/52/49 edges per lane
+    // in the CN phase and 56/53/41/40 in the VN phase; this gives 54/54/53/49 and 48/48/47/47. G is fixed by Z and the CTA
+    // size (qc_max_threads / 32 / ceil(Z / 32)), the same for every rule.
+    {
+        const int Zb_ = (Z + 31) / 32;
+        const int G = std::max(1, (qc_max_threads(0) / 32) / Zb_);
+        auto balance = [&](std::vector<int>& order, const std::vector<int>& deg, auto cls_of) {
+            std::vector<long long> load(G, 0);
+            size_t pos = 0;
+            while (pos < order.size()) {
+                size_t end = pos;
+                const int c = cls_of(order[pos]);
+                while (end < order.size() && cls_of(order[end]) == c) ++end;      // one class: positions [pos, end)
+                std::vector<int> items(order.begin() + pos, order.begin() + end);
+                std::stable_sort(items.begin(), items.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+                size_t next = 0;
+                for (size_t r0 = pos; r0 < end; r0 += G) {
+                    const size_t r1 = std::min(end, r0 + (size_t)G);
+                    std::vector<size_t> slots;
+                    for (size_t q = r0; q < r1; ++q) slots.push_back(q);
+                    std::stable_sort(slots.begin(), slots.end(), [&](size_t a, size_t b) { return load[a % G] < load[b % G]; });
+                    for (size_t q : slots) {
+                        order[q] = items[next++];
+                        load[q % G] += deg[order[q]];
+                    }
+                }
+                pos = end;
+            }
+        };
+        balance(rorder, rdeg, row_class);
+        balance(corder, cdeg, col_class);
+    }
     std::vector<int> row_cls_end(5, 0), col_cls_end(11, 0);
     for (int r = 0; r < n_rows; ++r) for (int k = row_class(r); k < 5; ++k) ++row_cls_end[k];
     for (int c = 0; c < n_cols; ++c) for (int k = col_class(c); k < 11; ++k) ++col_cls_end[k];

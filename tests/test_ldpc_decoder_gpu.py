@@ -286,3 +286,30 @@ def test_reference_order_layered(cuda_device):
     x = dec(torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
     ref = O.LDPC5GDecoderRef(enc_r, cn_update="minsum", cn_schedule="layered", hard_out=False, num_iter=6)
     assert np.array_equal(x, ref(llr, math_mode=0, order="reference", pure=True))
+
+
+@pytest.mark.parametrize("rule,ebno", [("boxplus-phi", 1.2), ("minsum", 1.4)])
+def test_full_batch_4096_bit_exact_vs_oracle(cuda_device, rule, ebno):
+    """configs[1] at its FULL size (batch 4096, n = 8448, 20 iterations) in the waterfall region, where converged and
+    non-converged codewords coexist: soft outputs of the QC kernel == oracle (kernel math, kernel order) for every one
+    of the 4096 x 8448 values; for min-sum additionally sum_order="reference" == the oracle build without sb_math.h."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    from bench import host_cores
+    k, n, bs = 4224, 8448, 4096
+    rng = np.random.default_rng(4096)
+    enc_r = O.LDPC5GEncoderRef(k, n)
+    u = rng.integers(0, 2, (bs, k))
+    llr = _noisy_llr(enc_r(u), ebno, k / n, rng)
+    enc = LDPC5GEncoder(k, n)
+    threads = host_cores()[0]
+    x = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20)(
+        torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+    ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20)
+    xr = ref(llr, math_mode=1, order="kernel", num_threads=threads)
+    assert np.array_equal(x, xr)
+    blk = ((x[:, :k] > 0) != (u > 0)).any(axis=1).mean()
+    assert 0.0 < blk < 1.0                                  # both converged and non-converged codewords are present
+    if rule == "minsum":
+        x2 = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20, sum_order="reference")(
+            torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
+        assert np.array_equal(x2, ref(llr, math_mode=0, order="reference", num_threads=threads, pure=True))

@@ -111,3 +111,39 @@ def test_config3_mimo_ofdm_lmmse_ldpc_link(cuda_device):
                  demapping="maxlog")
     ber2, _ = sim_ber(link2, [-6.0, 6.0], batch_size=64, max_mc_iter=1, verbose=False, early_stop=False)
     assert ber2[0] > ber2[1] and ber2[1] == 0
+
+
+@pytest.mark.parametrize("cfg", ["configs2_siso_2048", "configs3_mimo_1024"])
+def test_full_batch_receive_chain_vs_oracle(cuda_device, cfg):
+    """The oracle comparison of the receive chain at the configurations' FULL batch (configs[2]: 2048 frames, 64-QAM
+    app; configs[3]: 1024 frames, 4 streams x 16 antennas, 16-QAM app through the fused LinearDetector), LLRs of every
+    data resource element against the complex128 NumPy chain. LLRs scale with 1/no_eff, whose fp32 evaluation carries the
+    cancellation measured in test_lmmse_error_sits_inside_the_reference_fp32_envelope; the bar is therefore relative to
+    the largest LLR of the comparison set, and hard decisions must agree except on LLRs that are numerically zero."""
+    from sionna_b200.phy import config
+    config.seed = 11
+    if cfg == "configs2_siso_2048":
+        link, batch, ebno, m, streams = Link(1, 1, 6, 0.5), 2048, 18.0, 6, 1
+    else:
+        link, batch, ebno, m, streams = Link(4, 16, 4, 0.5, detector=True, tdl=True), 1024, 4.0, 4, 4
+    b, x, h, y, no = link.front_end(batch, ebno)
+    h_hat, ev = link.est(y, no)
+    if link.detector is not None:
+        llr = link.detector(y, h_hat, ev, no).cpu().numpy()
+    else:
+        x_hat, no_eff = link.eq(y, h_hat, ev, no)
+        llr = link.demapper(x_hat, no_eff).cpu().numpy()
+    mask, pil = link.rg.pilot_pattern.mask.astype(bool), link.rg.pilot_pattern.pilots
+    eff = F.eff_sc_ind(76, (5, 6), True)
+    y_eff = y.cpu().numpy()[..., eff].astype(complex)
+    hr, er = F.ls_estimate(y_eff, mask, pil, float(no))
+    hr, er = F.nn_interp(hr, mask, pil), F.nn_interp(er, mask, pil)
+    xr, nr = F.ofdm_lmmse_equalize(y_eff, hr, er, float(no), mask, F.stream_management([[1]], streams))
+    lr = M.demapper(xr.astype(np.complex64), nr.astype(np.float32), M.qam(m), "app")
+    assert llr.shape == lr.shape == (batch, 1, streams, link.rg.num_data_symbols * m)
+    ok = np.repeat(nr, m, axis=-1) < 1.0                     # not in a deep fade (LLR ~ 0 there, sign is noise)
+    scale = np.abs(lr[ok]).max()
+    err = np.abs(llr[ok] - lr[ok])
+    assert err.max() <= 2e-3 * scale and np.sqrt(np.mean(err ** 2)) <= 1e-4 * scale
+    sure = ok & (np.abs(lr) > 1e-3 * scale)
+    assert np.array_equal(llr[sure] > 0, lr[sure] > 0)
