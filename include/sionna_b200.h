@@ -175,6 +175,11 @@ int sb_count_errors(const float* d_b, const float* d_b_hat, int64_t rows, int32_
  * d_gen_rows[k]: row i of the reference's generator matrix (crc.py:126-156) packed MSB-first into 32 bits. */
 int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, int32_t k, int32_t crc_length, float* d_out,
                   int64_t rows, void* stream);
+/* CRCDecoder.call (fec/crc.py:300-327): d_x [rows, n] = [information bits | CRC parity]; d_gen_rows[n]: generator rows for
+ * an n-bit input (as for sb_crc_encode with k = n); d_valid[rows] = 1 iff re-encoding the whole word yields an all-zero
+ * parity; d_info [rows, n - crc_length] (optional) receives the information bits. */
+int sb_crc_check(const float* d_x, const uint32_t* d_gen_rows, int32_t n, int32_t crc_length, float* d_info,
+                 uint8_t* d_valid, int64_t rows, void* stream);
 /* TB5GScrambler.call (fec/scrambling.py:442-468): d_x [rows, n], d_seq [seq_rows, n] Gold sequence(s) (nr/utils.py:16-76);
  * binary != 0: |x - c|, else x * (1 - 2c); row r uses sequence r mod seq_rows. */
 int sb_scramble(const float* d_x, const float* d_seq, int32_t binary, float* d_out, int64_t rows, int32_t n,
@@ -212,7 +217,8 @@ int sb_ls_at_pilots(const float* d_y, const int32_t* d_pilot_ind, const float* d
                     int32_t grid_size, void* stream);
 /* LinearInterpolator._interpolate (ofdm/channel_estimation.py:657-734) with the index tables of :522-655:
  * d_h [batch, num_streams, num_pilots] -> d_out [batch, num_streams, num_symbols, num_subcarriers]; words = 2:
- * complex64 values (channel estimates), words = 1: fp32 values (error variances). */
+ * complex64 values (channel estimates), words = 1: fp32 values (error variances). time_avg: bit 0 = average the pilot
+ * symbols over time (lin_time_avg); bit 1 = floor fp32 results at 0 (the err_var clipping of channel_estimation.py:171). */
 int sb_interp_lin(const float* d_h, const int32_t* d_fx0, const int32_t* d_fx1, const int32_t* d_fy0,
                   const int32_t* d_fy1, const int32_t* d_ty0, const int32_t* d_ty1, const int32_t* d_npil,
                   int32_t time_avg, float* d_out, int64_t batch, int32_t num_streams, int32_t num_symbols,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sb_awgn": (i32, [vp, vp, i64, vp, i64, u64, u64, vp]),
     "sb_count_errors": (i32, [vp, vp, i64, i32, vp, vp]),
     "sb_crc_encode": (i32, [vp, vp, i32, i32, vp, i64, vp]),
+    "sb_crc_check": (i32, [vp, vp, i32, i32, vp, vp, i64, vp]),
     "sb_scramble": (i32, [vp, vp, i32, vp, i64, i32, i32, vp]),
     "sb_ofdm_modulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, i32, vp]),
     "sb_ofdm_demodulate": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, i32, i32, vp]),

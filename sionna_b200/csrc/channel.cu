@@ -131,29 +131,87 @@ __global__ void cir_link_scale_kernel(const float2* __restrict__ a, const float2
 }
 
 // h[row, t, j] = scale[link(row)] * sum_p a[row, p, t] e[tab(row), p, j]
-__global__ void cir_apply_kernel(const float2* __restrict__ a, const float2* __restrict__ e, long long e_link_stride,
-                                 const float* __restrict__ scale, float2* __restrict__ h, CirDims d, int F) {
+// A CTA owns a TILE_T x TILE_F tile of one antenna-pair row: the P x TILE_T taps and the P x TILE_F table entries are
+// staged in shared memory once, every thread accumulates RT x RJ outputs in registers (per path: RT + RJ shared loads
+// feed RT * RJ complex multiply-adds), so the kernel is bound by the FP32 pipe and by the single write of h instead of
+// by 2 * P loads per output. Two shapes: wide rows (OFDM: F = 76 ... 4096 subcarriers, few time steps) and narrow rows
+// (time channel: l_tot ~ 20 taps, thousands of time steps).
+template <int TILE_T, int RT, int TILE_F, int RJ>
+__global__ void __launch_bounds__((TILE_T / RT) * (TILE_F / RJ))
+cir_apply_kernel(const float2* __restrict__ a, const float2* __restrict__ e, long long e_link_stride,
+                 const float* __restrict__ scale, float2* __restrict__ h, CirDims d, int F, int tiles_t, int tiles_f) {
+    extern __shared__ float2 s_cir[];
+    constexpr int NTJ = TILE_F / RJ;                             // threads along the columns
+    float2* s_a = s_cir;                                          // [P][TILE_T]
+    float2* s_e = s_cir + (size_t)d.P * TILE_T;                   // [P][TILE_F]
+    const int tj = threadIdx.x % NTJ, tt = threadIdx.x / NTJ;
     const long long R = d.B * d.RX * d.RA * d.TX * d.TA;
-    for (long long rt = (long long)blockIdx.x * blockDim.y + threadIdx.y; rt < R * d.T; rt += (long long)gridDim.x * blockDim.y) {
-        const long long r = rt / d.T;
-        const int t = (int)(rt - r * d.T);
+    const long long n_tiles = R * tiles_t * tiles_f;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int ft = (int)(tile % tiles_f);
+        const int tq = (int)((tile / tiles_f) % tiles_t);
+        const long long r = tile / ((long long)tiles_f * tiles_t);
         const int tx = (int)((r / d.TA) % d.TX);
-        const long long brx = r / ((long long)d.TA * d.TX * d.RA);       // b * RX + rx
-        const long long link = brx * d.TX + tx;
+        const long long link = (r / ((long long)d.TA * d.TX * d.RA)) * d.TX + tx;   // (b * RX + rx) * TX + tx
         const float sc = scale ? scale[link] : 1.f;
-        const float2* ap = a + r * (long long)d.P * d.T + t;
+        const float2* ap = a + r * (long long)d.P * d.T;
         const float2* ep = e + link * e_link_stride;
-        float2* hp = h + rt * (long long)F;
-        for (int j = threadIdx.x; j < F; j += blockDim.x) {
-            float2 acc = make_float2(0.f, 0.f);
-            for (int p = 0; p < d.P; ++p) {
-                const float2 v = cmul_(ap[(size_t)p * d.T], ep[(size_t)p * F + j]);
-                acc.x += v.x;
-                acc.y += v.y;
+        const int t0 = tq * TILE_T, j0 = ft * TILE_F;
+        __syncthreads();
+        for (int i = threadIdx.x; i < d.P * TILE_T; i += blockDim.x) {
+            const int p = i / TILE_T, t = t0 + i % TILE_T;
+            s_a[i] = t < d.T ? ap[(size_t)p * d.T + t] : make_float2(0.f, 0.f);
+        }
+        for (int i = threadIdx.x; i < d.P * TILE_F; i += blockDim.x) {
+            const int p = i / TILE_F, j = j0 + i % TILE_F;
+            s_e[i] = j < F ? ep[(size_t)p * F + j] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        float2 acc[RT][RJ];
+#pragma unroll
+        for (int u = 0; u < RT; ++u)
+#pragma unroll
+            for (int v = 0; v < RJ; ++v) acc[u][v] = make_float2(0.f, 0.f);
+        for (int p = 0; p < d.P; ++p) {
+            float2 av[RT], ev[RJ];
+#pragma unroll
+            for (int u = 0; u < RT; ++u) av[u] = s_a[p * TILE_T + tt * RT + u];
+#pragma unroll
+            for (int v = 0; v < RJ; ++v) ev[v] = s_e[p * TILE_F + tj + v * NTJ];
+#pragma unroll
+            for (int u = 0; u < RT; ++u)
+#pragma unroll
+                for (int v = 0; v < RJ; ++v) {
+                    // explicit FMAs (the library is built with -fmad=false for the bit-exact decoder kernels)
+                    acc[u][v].x = fmaf(av[u].x, ev[v].x, fmaf(-av[u].y, ev[v].y, acc[u][v].x));
+                    acc[u][v].y = fmaf(av[u].x, ev[v].y, fmaf(av[u].y, ev[v].x, acc[u][v].y));
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < RT; ++u) {
+            const int t = t0 + tt * RT + u;
+            if (t >= d.T) continue;
+            float2* hp = h + (r * d.T + t) * (long long)F;
+#pragma unroll
+            for (int v = 0; v < RJ; ++v) {
+                const int j = j0 + tj + v * NTJ;
+                if (j < F) hp[j] = make_float2(acc[u][v].x * sc, acc[u][v].y * sc);
             }
-            hp[j] = make_float2(acc.x * sc, acc.y * sc);
         }
     }
+}
+
+template <int TILE_T, int RT, int TILE_F, int RJ>
+int launch_cir_apply(const float2* a, const float2* e, long long e_link_stride, const float* scale, float2* h, const CirDims& d,
+                     int F, cudaStream_t stream) {
+    auto kern = cir_apply_kernel<TILE_T, RT, TILE_F, RJ>;
+    const size_t smem = sizeof(float2) * (size_t)d.P * (TILE_T + TILE_F);
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_t = (d.T + TILE_T - 1) / TILE_T, tiles_f = (F + TILE_F - 1) / TILE_F;
+    const long long R = d.B * d.RX * d.RA * d.TX * d.TA;
+    kern<<<grid_cap(R * tiles_t * tiles_f), (TILE_T / RT) * (TILE_F / RJ), smem, stream>>>(a, e, e_link_stride, scale, h, d, F,
+                                                                                         tiles_t, tiles_f);
+    return SB_OK;
 }
 
 // out[b, i, c] = sum_j L[i, j] in[b, j, c]: i, j over the n antenna pairs (rx ant major), c over the (path, time) columns.
@@ -229,11 +287,15 @@ extern "C" int sb_cir_apply(const float* d_a, const float* d_e, int64_t e_link_s
     SB_CHECK_ARG(d_a && d_e && d_h && check_dims(batch, num_rx, num_rx_ant, num_tx, num_tx_ant, num_paths, num_time_steps) &&
                      num_cols > 0 && e_link_stride >= 0, "sb_cir_apply: bad arguments");
     CirDims d{batch, num_rx, num_rx_ant, num_tx, num_tx_ant, num_paths, num_time_steps};
-    const long long rows = batch * num_rx * num_rx_ant * (long long)num_tx * num_tx_ant * num_time_steps;
-    int tx = std::min(256, std::max(32, (num_cols + 31) / 32 * 32));
-    int ty = std::max(1, 256 / tx);
-    cir_apply_kernel<<<grid_cap((rows + ty - 1) / ty), dim3((unsigned)tx, (unsigned)ty, 1), 0, (cudaStream_t)stream>>>(
-        (const float2*)d_a, (const float2*)d_e, e_link_stride, d_scale, (float2*)d_h, d, num_cols);
+    SB_CHECK_ARG(num_paths <= 96, "sb_cir_apply: more than 96 paths are not supported");
+    int rc;
+    if (num_cols > 48)          // OFDM-like: wide rows
+        rc = launch_cir_apply<16, 2, 256, 8>((const float2*)d_a, (const float2*)d_e, e_link_stride, d_scale, (float2*)d_h, d,
+                                             num_cols, (cudaStream_t)stream);
+    else                        // time-channel-like: a few taps, many time steps
+        rc = launch_cir_apply<128, 8, 32, 2>((const float2*)d_a, (const float2*)d_e, e_link_stride, d_scale, (float2*)d_h, d,
+                                             num_cols, (cudaStream_t)stream);
+    if (rc) return rc;
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -390,6 +390,8 @@ __device__ __forceinline__ float lerp_c(float x, float x0, float x1, float y0, f
 }
 __device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); }
 __device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float2 vfloor0(float2 a) { return a; }            // only real error variances are floored
+__device__ __forceinline__ float vfloor0(float a) { return fmaxf(a, 0.f); }
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return cadd(a, b); }
 __device__ __forceinline__ float vadd(float a, float b) { return a + b; }
 __device__ __forceinline__ float2 vdiv(float2 a, float n) { return make_float2(a.x / n, a.y / n); }
@@ -410,8 +412,10 @@ __device__ __forceinline__ T freq_interp(const T* hp, const int* fx0, const int*
 template <typename T>
 __global__ void interp_lin_kernel(const T* __restrict__ h, const int* __restrict__ fx0, const int* __restrict__ fx1,
                                   const int* __restrict__ fy0, const int* __restrict__ fy1, const int* __restrict__ ty0,
-                                  const int* __restrict__ ty1, const int* __restrict__ npil, int time_avg,
+                                  const int* __restrict__ ty1, const int* __restrict__ npil, int flags,
                                   T* __restrict__ out, long long B, int TS, int S, int F, int P) {
+    const int time_avg = flags & 1;
+    const bool floor0 = (flags & 2) != 0;                       // error variances: max(., 0) after interpolation (:171)
     const int SF = S * F;
     const long long rows = B * TS;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -423,7 +427,8 @@ __global__ void interp_lin_kernel(const T* __restrict__ h, const int* __restrict
             if (time_avg) {
                 T acc = vzero(T());
                 for (int s2 = 0; s2 < S; ++s2) acc = vadd(acc, freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s2 * F + f, f));
-                const T v = vdiv(acc, (float)npil[ts]);        // every symbol carries the average: time interpolation is flat
+                T v = vdiv(acc, (float)npil[ts]);              // every symbol carries the average: time interpolation is flat
+                if (floor0) v = vfloor0(v);
                 for (int s = 0; s < S; ++s) op[s * F + f] = v;
             } else {
                 int last0 = -1, last1 = -1;
@@ -432,7 +437,9 @@ __global__ void interp_lin_kernel(const T* __restrict__ h, const int* __restrict
                     const int s0 = ty0[ts * S + s], s1 = ty1[ts * S + s];
                     if (s0 != last0) { y0 = freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s0 * F + f, f); last0 = s0; }
                     if (s1 != last1) { y1 = freq_interp<T>(hp, fx0, fx1, fy0, fy1, base + s1 * F + f, f); last1 = s1; }
-                    op[s * F + f] = lerp_c((float)s, (float)s0, (float)s1, y0, y1);
+                    T v = lerp_c((float)s, (float)s0, (float)s1, y0, y1);
+                    if (floor0) v = vfloor0(v);
+                    op[s * F + f] = v;
                 }
             }
         }

@@ -393,6 +393,25 @@ __global__ void crc_encode_kernel(const float* __restrict__ bits, const unsigned
     }
 }
 
+// CRCDecoder.call (fec/crc.py:300-327): the whole word [info | parity] (n bits) is run through the encoder again and the
+// check passes iff the new parity is all zero. One warp per row; also copies the n - L information bits.
+__global__ void crc_check_kernel(const float* __restrict__ x, const unsigned* __restrict__ gtab, int n, int L,
+                                 float* __restrict__ info, unsigned char* __restrict__ valid, long long rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int k = n - L;
+    for (long long r = (long long)blockIdx.x * nwarps + warp; r < rows; r += (long long)gridDim.x * nwarps) {
+        const float* b = x + r * (long long)n;
+        unsigned acc = 0;
+        for (int i = lane; i < n; i += 32) {
+            float v = b[i];
+            if (info && i < k) info[r * (long long)k + i] = v;
+            if (((int)v) & 1) acc ^= gtab[i];
+        }
+        acc = __reduce_xor_sync(0xffffffffu, acc);
+        if (lane == 0) valid[r] = acc == 0u ? 1 : 0;
+    }
+}
+
 // TB5GScrambler.call (fec/scrambling.py:442-468): binary: |x - c|; soft values: x * (1 - 2c). seq has seq_rows rows
 // (one per stream) of length n; row r of x uses seq row (r mod seq_rows).
 __global__ void scramble_kernel(const float* __restrict__ x, const float* __restrict__ seq, int binary,
@@ -523,6 +542,16 @@ extern "C" int sb_crc_encode(const float* d_bits, const uint32_t* d_gen_rows, in
                  "sb_crc_encode: bad arguments");
     if (rows == 0) return SB_OK;
     crc_encode_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(d_bits, d_gen_rows, k, crc_length, d_out, rows);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_crc_check(const float* d_x, const uint32_t* d_gen_rows, int32_t n, int32_t crc_length, float* d_info,
+                            uint8_t* d_valid, int64_t rows, void* stream) {
+    if (rows == 0) return SB_OK;
+    SB_CHECK_ARG(d_x && d_gen_rows && d_valid && crc_length >= 1 && crc_length <= 32 && n >= crc_length && rows >= 0,
+                 "sb_crc_check: bad arguments");
+    crc_check_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_gen_rows, n, crc_length, d_info, d_valid, rows);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -99,6 +99,7 @@ class CRCDecoder(Block):
         super().__init__(precision=precision, **kwargs)
         assert isinstance(crc_encoder, CRCEncoder), "crc_encoder must be a CRCEncoder instance."
         self._encoder = CRCEncoder(crc_encoder.crc_degree, precision=precision)
+        self._tab = None
 
     @property
     def crc_degree(self):
@@ -113,8 +114,18 @@ class CRCDecoder(Block):
             raise ValueError("Input length must be greater than or equal to the CRC length.")
 
     def call(self, x_crc, /):
-        L = self._encoder.crc_length
-        x_info = x_crc[..., :-L]
-        x_parity = self._encoder(x_crc)[..., -L:]
-        crc_check = x_parity.sum(dim=-1, keepdim=True) <= 0
-        return x_info, crc_check
+        """One kernel (``sb_crc_check``): parity of the re-encoded word, validity flag and the information bits."""
+        if self.precision != "single":
+            raise NotImplementedError("sb_crc_check is an fp32 kernel.")
+        enc = self._encoder
+        L, n = enc.crc_length, x_crc.shape[-1]
+        dev = self.device
+        if self._tab is None or self._tab[0] != n or self._tab[1].device != dev:
+            self._tab = (n, torch.from_numpy(enc._gen_rows(n).view(np.int32)).to(dev))
+        x = x_crc.to(device=dev, dtype=torch.float32).contiguous()
+        rows = x.numel() // n
+        info = torch.empty(list(x.shape[:-1]) + [n - L], dtype=torch.float32, device=dev)
+        valid = torch.empty(list(x.shape[:-1]) + [1], dtype=torch.bool, device=dev)
+        check(lib().sb_crc_check(ptr(x), ptr(self._tab[1]), n, L, ptr(info), ptr(valid), rows, current_stream()),
+              "sb_crc_check")
+        return info.to(x_crc.dtype) if x_crc.dtype.is_floating_point else info, valid

@@ -51,7 +51,7 @@ class NearestNeighborInterpolator(BaseChannelInterpolator):
         self._shape = mask_shape
         self._dev = None
 
-    def _interpolate(self, x):
+    def _interpolate(self, x, floor0=False):
         tx, st, s_, f_ = self._shape
         ts = tx * st
         if self._dev is None or self._dev.device != x.device:
@@ -63,6 +63,10 @@ class NearestNeighborInterpolator(BaseChannelInterpolator):
 
     def __call__(self, h_hat, err_var):
         return self._interpolate(h_hat), self._interpolate(err_var)
+
+    def interpolate_floored(self, h_hat, err_var):
+        """Same, with the estimator's ``max(err_var, 0)`` (:171) applied inside the error-variance kernel."""
+        return self._interpolate(h_hat), self._interpolate(err_var, floor0=True)
 
 
 class LinearInterpolator(BaseChannelInterpolator):
@@ -125,7 +129,7 @@ class LinearInterpolator(BaseChannelInterpolator):
         self._tabs_np = [np.ascontiguousarray(t, np.int32) for t in (x0, x1, y0 + 1, y1 + 1, t0, t1, npil)]
         self._tabs = None
 
-    def _interpolate(self, x):
+    def _interpolate(self, x, floor0=False):
         tx, st, s_, f_ = self._shape
         ts = tx * st
         if self._tabs is None or self._tabs[0].device != x.device:
@@ -137,13 +141,18 @@ class LinearInterpolator(BaseChannelInterpolator):
         out = torch.empty((b, ts, s_, f_), dtype=xin.dtype, device=x.device)
         t = self._tabs
         check(lib().sb_interp_lin(ptr(xin), ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), ptr(t[4]), ptr(t[5]), ptr(t[6]),
-                                  int(self._time_avg), ptr(out), b, ts, s_, f_, p, 2 if cplx else 1, current_stream()),
+                                  int(self._time_avg) | (2 if (floor0 and not cplx) else 0), ptr(out), b, ts, s_, f_, p,
+                                  2 if cplx else 1, current_stream()),
               "sb_interp_lin")
         return out.reshape(lead + [tx, st, s_, f_])
 
     def __call__(self, h_hat, err_var):
         # the reference interpolates err_var as a complex tensor and keeps the real part (:729-732); same values in fp32
         return self._interpolate(h_hat), self._interpolate(err_var)
+
+    def interpolate_floored(self, h_hat, err_var):
+        """Same, with the estimator's ``max(err_var, 0)`` (:171) applied inside the error-variance kernel."""
+        return self._interpolate(h_hat), self._interpolate(err_var, floor0=True)
 
 
 class BaseChannelEstimator(Block):
@@ -217,6 +226,11 @@ class LSChannelEstimator(BaseChannelEstimator):
         shp = lead + [pp.num_tx, pp.num_streams_per_tx, pp.num_pilot_symbols]
         h, err = h.reshape(shp), err.reshape(shp)
         if self._interpolation_type is not None:
-            h, err = self._interpol(h, err)
-            err = torch.clamp(err, min=0.0)                                      # :171
+            if isinstance(self._interpol, LinearInterpolator):
+                h, err = self._interpol.interpolate_floored(h, err)            # max(err_var, 0) of :171 inside the kernel
+            elif isinstance(self._interpol, NearestNeighborInterpolator):
+                h, err = self._interpol(h, err)                                # a gather of no / |p|^2 >= 0: nothing to floor
+            else:
+                h, err = self._interpol(h, err)
+                err = torch.clamp(err, min=0.0)                                  # :171 (user-supplied interpolator)
         return h, err
