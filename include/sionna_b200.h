@@ -117,6 +117,29 @@ int sb_ldpc_decode(const sb_ldpc_graph* g, const float* d_llr, int64_t batch, in
                    const float* d_state_in, float* d_state_out, float* d_out,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Unfused belief propagation (csrc/ldpc_bp_flat.cu): one call per half-iteration on [num_edges, batch] message tensors
+ * in the reference's layouts, for decoders with Python callbacks (`v2c_callbacks` / `c2v_callbacks`, decoding.py:484-486,
+ * 513-515) or user-supplied node updates. msg_v2c is in VN order (edge e of decoding.py:286-288), msg_c2v in CN-view
+ * order (position j holds edge v2c_perm[j], decoding.py:329); node reductions run in those list orders.
+ *   sb_ldpc_flat_init: d_x [batch, num_vn] channel logits after rate recovery and clipping (a 0-iteration sb_ldpc_decode)
+ *       -> d_llr [num_vn, batch] = -x (decoding.py:565), d_v2c [num_edges, batch] = llr of the edge's VN (:571) or
+ *       -d_state_in [num_edges, batch] (:573).
+ *   sb_ldpc_flat_cn: CN update (rule as in sb_ldpc_decode) of the check nodes d_cn_list[num_nodes] (NULL: nodes
+ *       0..num_nodes-1), reading d_v2c, writing those nodes' positions of d_c2v.
+ *   sb_ldpc_flat_vn: VN update of every variable node: d_v2c, d_xhat [num_vn, batch] (clipped x_tot, internal sign).
+ *   sb_ldpc_flat_out: d_out [batch, n_out] from d_xhat rows d_out_vn[n_out] (hard / soft as sb_ldpc_decode); optional
+ *       d_state_out [num_edges, batch] = -d_v2c (:636). */
+int sb_ldpc_flat_init(const float* d_x, const int32_t* d_vn_of_edge, const float* d_state_in, float* d_llr, float* d_v2c,
+                      int64_t batch, int32_t num_vn, int32_t num_edges, void* stream);
+int sb_ldpc_flat_cn(const float* d_v2c, float* d_c2v, const int32_t* d_cn_ptr, const int32_t* d_v2c_perm,
+                    const int32_t* d_cn_list, int32_t num_nodes, int64_t batch, int32_t cn_rule, float offset,
+                    float llr_max, void* stream);
+int sb_ldpc_flat_vn(const float* d_c2v, const float* d_llr, const int32_t* d_vn_ptr, const int32_t* d_c2v_perm,
+                    float* d_v2c, float* d_xhat, int32_t num_vn, int64_t batch, int32_t vn_rule, float llr_max,
+                    void* stream);
+int sb_ldpc_flat_out(const float* d_xhat, const int32_t* d_out_vn, float* d_out, const float* d_v2c, float* d_state_out,
+                     int64_t batch, int32_t n_out, int32_t num_edges, int32_t hard_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 5G NR LDPC encoder with rate matching
  * replaces LDPC5GEncoder.call / _encode_fast / _matmul_gather   fec/ldpc/encoding.py:599-668, 572-591, 559-570

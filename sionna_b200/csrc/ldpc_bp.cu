@@ -28,6 +28,7 @@
 #include "sb_common.h"
 #include "sb_math.h"
 #include "ldpc_graph.h"
+#include "ldpc_rules.cuh"
 
 namespace {
 
@@ -53,128 +54,16 @@ struct BpParams {
     float* ws;
 };
 
-// ---- check-node updates: v2c -> c2v for the CN with rank r (deg edges at slots off[l] + r) -----------
-// boxplus-phi, decoding.py:1126-1166
-__device__ __forceinline__ void cn_phi(const float* v2c, float* c2v, const int* off, int deg, int r, float clip) {
-    float P = 0.f;
-    unsigned par = 0;
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        float x = v2c[s];
-        unsigned neg = x < 0.f;                         // sign(0) := +1 (:1129)
-        par ^= neg;
-        float p = sb_phif(fabsf(x));                    // >= 0 for every input (tests/test_sb_math.py)
-        P = __fadd_rn(P, p);                            // :1150 sequential sum
-        c2v[s] = neg ? -p : p;                          // stage phi(|x|), sign bit carries sign(x)
-    }
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        unsigned bits = __float_as_uint(c2v[s]);
-        unsigned neg = bits >> 31;
-        float p = __uint_as_float(bits & 0x7fffffffu);
-        float y = sb_phif(__fadd_rn(-p, P));            // :1155-1161
-        y = (neg ^ par) ? -y : y;                       // extrinsic sign = sign(x_e) * prod(signs)
-        c2v[s] = clipf(y, clip);                        // :1163
-    }
-}
-
-// boxplus (tanh), decoding.py:1000-1043
-__device__ __forceinline__ void cn_tanh(const float* v2c, float* c2v, const int* off, int deg, int r, float clip) {
-    const float atanh_clip = (float)(1 - 1e-7);
-    float prod = 1.f;
-#pragma unroll 2
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        float t = sb_tanhf(__fmul_rn(v2c[s], 0.5f));    // x/2 == x*0.5 exactly
-        if (t == 0.f) t = 1e-12f;
-        prod = __fmul_rn(prod, t);
-        c2v[s] = t;
-    }
-#pragma unroll 2
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        float e = __fmul_rn(__fdiv_rn(1.f, c2v[s]), prod);
-        if (fabsf(e) < 1e-7f) e = 0.f;
-        e = clipf(e, atanh_clip);
-        float y = __fmul_rn(2.f, sb_atanhf(e));
-        c2v[s] = clipf(y, clip);
-    }
-}
-
-// (offset-)min-sum, decoding.py:796-909. The reference's "subtract min, replace zeros by 1e5, take the
-// min again, detect duplicate minima through the row sum" sequence is reproduced exactly:
-//   unique minimum  -> that edge gets fl(fl(m2 - m1) + m1), every other edge m1
-//   repeated minimum-> every edge gets m1
-// A slow path redoes the reference's row sum literally when magnitudes are large enough (>= ~1e5/deg)
-// for the sum test or the "== 1e5" test to behave differently.
-__device__ __forceinline__ void cn_minsum(const float* v2c, float* c2v, const int* off, int deg, int r, float clip,
-                                          float offset) {
-    const float large_val = 100000.f;
-    float m1 = INFINITY, m2 = INFINITY, amax = 0.f;
-    unsigned par = 0;
-    int cnt = 0;
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        float x = clipf(v2c[off[l] + r], large_val);    // :808
-        par ^= (unsigned)(x < 0.f);
-        float a = fabsf(x);
-        amax = fmaxf(amax, a);
-        if (a < m1) { m2 = m1; m1 = a; cnt = 1; }
-        else if (a == m1) { ++cnt; m2 = m1; }
-        else if (a < m2) { m2 = a; }
-    }
-    float min_e;                                        // value written at the minimum position(s)
-    bool literal = (float)(deg - 1) * (amax - m1) >= 99000.f;
-    if (!literal) {
-        min_e = (cnt >= 2) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);   // :863, :876
-        if (deg == 1) min_e = __fadd_rn(large_val, m1);               // single edge: min over {1e5}
-    } else {
-        float min2 = INFINITY, node_sum = 0.f;
-        for (int l = 0; l < deg; ++l) {
-            float a = fabsf(clipf(v2c[off[l] + r], large_val));
-            float d = __fsub_rn(a, m1);
-            if (d == 0.f) d = large_val;
-            min2 = fminf(min2, d);
-            node_sum = __fadd_rn(node_sum, d);
-        }
-        float min_val_2 = __fadd_rn(min2, m1);
-        node_sum = __fsub_rn(node_sum, 199999.f);
-        float sg = node_sum > 0.f ? 1.f : (node_sum < 0.f ? -1.f : 0.f);
-        float dm = __fmul_rn(0.5f, __fsub_rn(1.f, sg));
-        min_e = __fadd_rn(__fmul_rn(__fsub_rn(1.f, dm), m1), __fmul_rn(dm, min_val_2));
-    }
-#pragma unroll 4
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        float x = clipf(v2c[s], large_val);
-        unsigned neg = x < 0.f;
-        float a = fabsf(x);
-        bool at_min = literal ? (__fsub_rn(a, m1) == 0.f || __fsub_rn(a, m1) == large_val) : (a == m1);
-        float m = at_min ? min_e : m1;                  // :886
-        m = fmaxf(__fsub_rn(m, offset), 0.f);           // :895
-        m = (neg ^ par) ? -m : m;                       // :903
-        c2v[s] = clipf(m, clip);                        // :906
-    }
-}
-
-__device__ __forceinline__ void cn_identity(const float* v2c, float* c2v, const int* off, int deg, int r) {
-    for (int l = 0; l < deg; ++l) {
-        int s = off[l] + r;
-        c2v[s] = v2c[s];
-    }
-}
-
-template <int RULE>
-__device__ __forceinline__ void cn_node(const float* v2c, float* c2v, const int* off, int deg, int r, float clip,
-                                        float offset) {
-    if (RULE == SB_CN_BOXPLUS_PHI) cn_phi(v2c, c2v, off, deg, r, clip);
-    else if (RULE == SB_CN_BOXPLUS) cn_tanh(v2c, c2v, off, deg, r, clip);
-    else if (RULE == SB_CN_MINSUM) cn_minsum(v2c, c2v, off, deg, r, clip, 0.f);
-    else if (RULE == SB_CN_OFFSET_MINSUM) cn_minsum(v2c, c2v, off, deg, r, clip, offset);
-    else cn_identity(v2c, c2v, off, deg, r);
-}
+// ---- check-node updates (ldpc_rules.cuh) on the slot layout: l-th edge of the CN with rank r at off[l] + r ---------
+struct SlotEdges {
+    const float* v2c;
+    float* c2v;
+    const int* off;
+    int r;
+    __device__ __forceinline__ float in(int l) const { return v2c[off[l] + r]; }
+    __device__ __forceinline__ void out(int l, float v) const { c2v[off[l] + r] = v; }
+    __device__ __forceinline__ float staged(int l) const { return c2v[off[l] + r]; }
+};
 
 // degree of rank r given non-increasing level counts; `deg` is a hint from the previous (smaller) rank
 __device__ __forceinline__ int rank_degree(const int* cnt, int L, int r, int deg) {
@@ -286,7 +175,7 @@ __global__ void __launch_bounds__(1024, 1) ldpc_bp_kernel(const __grid_constant_
                         int r = p.sched ? p.sched[(size_t)j * p.n_active + i] : i;
                         if (p.sched) { deg = 0; while (deg < p.Lc && r < s_cn_cnt[deg]) ++deg; }
                         else deg = rank_degree(s_cn_cnt, p.Lc, r, deg);
-                        cn_node<RULE>(v2c, c2v, s_cn_off, deg, r, clip, p.offset);
+                        cn_node<RULE>(SlotEdges{v2c, c2v, s_cn_off, r}, deg, clip, p.offset);
                     }
                 }
                 __syncthreads();

@@ -109,6 +109,11 @@ class LDPCBPDecoder(Block):
     state when ``return_state`` is set. ``cn_update`` is one of ``"boxplus-phi"`` (default), ``"boxplus"``,
     ``"minsum"`` / ``"min"``, ``"offset-minsum"``, ``"identity"``; ``vn_update`` one of ``"sum"``, ``"identity"``.
 
+    ``cn_update`` / ``vn_update`` may also be callables on ragged messages and ``v2c_callbacks`` / ``c2v_callbacks``
+    lists of callables (decoding.py:79-126; `sionna_b200.phy.fec.ldpc.utils.RaggedMessages` plays the role of the
+    ragged tensor): such decoders run the unfused path - one kernel launch per half-iteration on ``[num_edges, batch]``
+    tensors in the reference's layouts and list orders - instead of the fused shared-memory kernels.
+
     Extension (keyword ``sum_order``, not in the reference): ``"ascending"`` (default) combines the messages of a node
     in ascending neighbour index, which the quasi-cyclic fast path needs; ``"reference"`` walks them in the reference's
     own list orders (``np.argsort`` results of decoding.py:286, 329) on the generic kernel. fp32 sums depend on their
@@ -152,15 +157,21 @@ class LDPCBPDecoder(Block):
         self._num_cns, self._num_vns = pcm.shape[0], pcm.shape[1]
         self._llr_max = float(llr_max)
 
-        for name, cbs in (("v2c_callbacks", v2c_callbacks), ("c2v_callbacks", c2v_callbacks)):
-            if cbs is None or (isinstance(cbs, (list, tuple)) and len(cbs) == 0):
-                continue
-            if isinstance(cbs, (list, tuple, types.FunctionType)):
-                raise NotImplementedError(
-                    f"{name}: per-iteration Python callbacks need the unfused message path, which this build "
-                    "does not provide; the fused sm_100a kernel keeps messages in shared memory.")
+        # callbacks / callable node updates (decoding.py:79-126): honoured on the unfused path (one launch per
+        # half-iteration, csrc/ldpc_bp_flat.cu); the fused kernels run when neither is given
+        def _cb_list(name, cbs):
+            if cbs is None:
+                return []
+            if isinstance(cbs, (list, tuple)):
+                for c in cbs:
+                    if not callable(c):
+                        raise TypeError(f"{name} must be a list of callables.")
+                return list(cbs)
+            if callable(cbs):
+                return [cbs]
             raise TypeError(f"{name} must be a list of callables.")
-        self._v2c_callbacks, self._c2v_callbacks = [], []
+        self._v2c_callbacks = _cb_list("v2c_callbacks", v2c_callbacks)
+        self._c2v_callbacks = _cb_list("c2v_callbacks", c2v_callbacks)
 
         schedule = None
         if isinstance(cn_schedule, str) and cn_schedule == "flooding":
@@ -189,18 +200,21 @@ class LDPCBPDecoder(Block):
         self._vn_idx = self._vn_idx[idx]
         self._num_edges = len(self._vn_idx)
 
+        self._cn_fn = self._vn_fn = None
         if isinstance(cn_update, str) and cn_update in _CN_RULES:
             self._cn_rule = _CN_RULES[cn_update]
-        elif isinstance(cn_update, types.FunctionType):
-            raise NotImplementedError("callable cn_update needs the unfused message path (not provided).")
+        elif callable(cn_update):
+            self._cn_rule, self._cn_fn = _CN_RULES["identity"], cn_update
         else:
             raise TypeError("Provided cn_update not supported.")
         if isinstance(vn_update, str) and vn_update in _VN_RULES:
             self._vn_rule = _VN_RULES[vn_update]
-        elif isinstance(vn_update, types.FunctionType):
-            raise NotImplementedError("callable vn_update needs the unfused message path (not provided).")
+        elif callable(vn_update):
+            self._vn_rule, self._vn_fn = _VN_RULES["identity"], vn_update
         else:
             raise TypeError("Provided vn_update not supported.")
+        self._unfused = bool(self._v2c_callbacks or self._c2v_callbacks or self._cn_fn or self._vn_fn)
+        self._flat = None                                   # device index tables of the unfused path (lazy)
         self._offset = 0.5  # default of cn_update_offset_minsum (decoding.py:755)
 
         in_map, n_in, out_vn, n_out = self._io_maps()
@@ -272,9 +286,119 @@ class LDPCBPDecoder(Block):
     def build(self, input_shape, **kwargs):
         assert input_shape[-1] == self._num_vns, "Last dimension must be of length n."
 
+    # ---- unfused path: callbacks / callable node updates ------------------------------------------------------
+    def _flat_tables(self, dev):
+        """Index tensors of the reference's message layouts (decoding.py:277-345) on `dev`."""
+        if self._flat is not None and self._flat["dev"] == dev:
+            return self._flat
+        e, n, c = self._num_edges, self._num_vns, self._num_cns
+        v2c_perm = np.argsort(self._cn_idx)                               # :329 CN view: position j <- edge v2c_perm[j]
+        c2v_perm = np.argsort(v2c_perm)                                   # :336 edge e -> its CN-view position
+        vn_ptr = np.zeros(n + 1, np.int64)
+        np.cumsum(np.bincount(self._vn_idx, minlength=n), out=vn_ptr[1:])
+        cn_ptr = np.zeros(c + 1, np.int64)
+        np.cumsum(np.bincount(self._cn_idx, minlength=c), out=cn_ptr[1:])
+        _, _, out_vn, n_out = self._io_maps()
+        out_vn = np.arange(n) if out_vn is None else np.asarray(out_vn)
+
+        def t32(a):
+            return torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
+        f = {"dev": dev, "v2c_perm": t32(v2c_perm), "c2v_perm": t32(c2v_perm), "vn_ptr": t32(vn_ptr), "cn_ptr": t32(cn_ptr),
+             "vn_of_edge": t32(self._vn_idx), "out_vn": t32(out_vn), "n_out": int(len(out_vn)),
+             "vn_splits": torch.from_numpy(vn_ptr).to(dev), "cn_splits": torch.from_numpy(cn_ptr).to(dev),
+             "v2c_perm64": torch.from_numpy(v2c_perm.astype(np.int64)).to(dev),
+             "c2v_perm64": torch.from_numpy(c2v_perm.astype(np.int64)).to(dev)}
+        if self._scheduling != "flooding":
+            subs = []
+            for row in self._cn_schedule:                                  # active CNs of every sub-iteration
+                pos = np.concatenate([np.arange(cn_ptr[cn], cn_ptr[cn + 1]) for cn in row]) if len(row) else np.zeros(0, np.int64)
+                lens = np.array([cn_ptr[cn + 1] - cn_ptr[cn] for cn in row], np.int64)
+                splits = np.concatenate([[0], np.cumsum(lens)])
+                subs.append({"cns": t32(row), "pos": torch.from_numpy(pos.astype(np.int64)).to(dev),
+                             "splits": torch.from_numpy(splits).to(dev)})
+            f["subs"] = subs
+        # rate recovery + clipping through a 0-iteration launch of the fused kernel with an identity output map
+        in_map, n_in, _, _ = self._io_maps()
+        f["rr_graph"] = self._graph if in_map is None else _GraphHandle(c, n, self._cn_idx, self._vn_idx, in_map, n_in)
+        self._flat = f
+        return f
+
+    def _decode_unfused(self, llr2d, num_iter, msg_v2c):
+        from .utils import RaggedMessages
+        L = lib()
+        dev, b = llr2d.device, llr2d.shape[0]
+        f = self._flat_tables(dev)
+        e, n, c = self._num_edges, self._num_vns, self._num_cns
+        st = current_stream()
+        # [B, N] clipped channel logits incl. punctured / filler positions (decoding.py:552-554, 1444-1475)
+        g = f["rr_graph"]
+        x0 = torch.empty((b, n), dtype=torch.float32, device=dev)
+        ws, ws_bytes = g.workspace(dev)
+        check(L.sb_ldpc_decode(g.handle, ptr(llr2d), b, 0, self._cn_rule, self._vn_rule, self._offset, self._llr_max, 0,
+                               None, None, ptr(x0), ptr(ws), ws_bytes, st), "sb_ldpc_decode (rate recovery)")
+        st_in = None
+        if msg_v2c is not None:
+            st_in = torch.as_tensor(msg_v2c).to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(st_in.shape) != (e, b):
+                raise ValueError("msg_v2c must have shape [num_edges, batch_size].")
+        llr = torch.empty((n, b), dtype=torch.float32, device=dev)
+        v2c = torch.empty((e, b), dtype=torch.float32, device=dev)
+        c2v = torch.zeros((e, b), dtype=torch.float32, device=dev)                                  # :581
+        xhat = llr                                                                                  # :607 (0 iterations)
+        check(L.sb_ldpc_flat_init(ptr(x0), ptr(f["vn_of_edge"]), ptr(st_in), ptr(llr), ptr(v2c), b, n, e, st),
+              "sb_ldpc_flat_init")
+        xbuf = torch.empty((n, b), dtype=torch.float32, device=dev)
+        subs = f.get("subs") or [None]
+        for it in range(int(num_iter)):
+            for sub in subs:
+                # ---- CN update of the active nodes (:479-483) ---------------------------------------------------
+                if self._cn_fn is not None:
+                    msg_in = v2c.index_select(0, f["v2c_perm64"] if sub is None else f["v2c_perm64"].index_select(0, sub["pos"]))
+                    rag = RaggedMessages(msg_in, f["cn_splits"] if sub is None else sub["splits"])
+                    rag = self._cn_fn(rag, self._llr_max)
+                else:
+                    check(L.sb_ldpc_flat_cn(ptr(v2c), ptr(c2v), ptr(f["cn_ptr"]), ptr(f["v2c_perm"]),
+                                            None if sub is None else ptr(sub["cns"]),
+                                            c if sub is None else int(sub["cns"].numel()), b, self._cn_rule, self._offset,
+                                            self._llr_max, st), "sb_ldpc_flat_cn")
+                    rag = None
+                    if self._c2v_callbacks:
+                        rag = RaggedMessages(c2v if sub is None else c2v.index_select(0, sub["pos"]),
+                                             f["cn_splits"] if sub is None else sub["splits"])
+                for cb in self._c2v_callbacks:                                                      # :484-486
+                    rag = cb(rag, it)
+                if rag is not None:
+                    vals = rag.flat_values.to(torch.float32)
+                    if sub is None:
+                        c2v = vals.contiguous()                                                     # :500
+                    else:
+                        c2v.index_copy_(0, sub["pos"], vals)                                        # :489-497
+                # ---- full VN update (:506-511) -------------------------------------------------------------------
+                if self._vn_fn is not None:
+                    rag_v = RaggedMessages(c2v.index_select(0, f["c2v_perm64"]), f["vn_splits"])
+                    rag_v, xhat = self._vn_fn(rag_v, llr, self._llr_max)
+                    v2c = rag_v.flat_values.to(torch.float32).contiguous()
+                    xhat = xhat.to(torch.float32).contiguous()
+                else:
+                    check(L.sb_ldpc_flat_vn(ptr(c2v), ptr(llr), ptr(f["vn_ptr"]), ptr(f["c2v_perm"]), ptr(v2c), ptr(xbuf),
+                                            n, b, self._vn_rule, self._llr_max, st), "sb_ldpc_flat_vn")
+                    xhat = xbuf
+                if self._v2c_callbacks:                                                             # :513-515
+                    rag_v = RaggedMessages(v2c, f["vn_splits"])
+                    for cb in self._v2c_callbacks:
+                        rag_v = cb(rag_v, it + 1, xhat)
+                    v2c = rag_v.flat_values.to(torch.float32).contiguous()
+        out = torch.empty((b, f["n_out"]), dtype=torch.float32, device=dev)
+        st_out = torch.empty((e, b), dtype=torch.float32, device=dev) if self._return_state else None
+        check(L.sb_ldpc_flat_out(ptr(xhat), ptr(f["out_vn"]), ptr(out), ptr(v2c), ptr(st_out), b, f["n_out"], e,
+                                 int(self._hard_out), st), "sb_ldpc_flat_out")
+        return out, st_out
+
     def _decode(self, llr2d, num_iter, msg_v2c):
         if self.precision != "single":
             raise NotImplementedError("sb_ldpc_decode is an fp32 kernel; precision='double' is not available.")
+        if self._unfused:
+            return self._decode_unfused(llr2d, num_iter, msg_v2c)
         g = self._graph
         dev = llr2d.device
         b = llr2d.shape[0]
