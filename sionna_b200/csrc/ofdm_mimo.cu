@@ -26,6 +26,7 @@
 #include <mutex>
 #include <vector>
 #include "rng.cuh"
+#include "lmmse_diag.cuh"
 
 namespace {
 
@@ -703,59 +704,14 @@ __global__ void __launch_bounds__(128, 6) ofdm_lmmse_diag_kernel(const OfdmEqPar
                 for (int c = 0; c <= a; ++c) Bm[a * (a + 1) / 2 + c] = cadd(Bm[a * (a + 1) / 2 + c], cmulc(hw[c], hw[a]));
             }
         }
-        // A = B + I = C C^H (lower, in registers)
-        float2 C[K * (K + 1) / 2];
-#pragma unroll
-        for (int e = 0; e < K * (K + 1) / 2; ++e) C[e] = Bm[e];
-#pragma unroll
-        for (int a = 0; a < K; ++a) C[a * (a + 1) / 2 + a].x += 1.f;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            float dj = C[j * (j + 1) / 2 + j].x;
-#pragma unroll
-            for (int k = 0; k < j; ++k) { float2 l = C[j * (j + 1) / 2 + k]; dj -= l.x * l.x + l.y * l.y; }
-            dj = sqrtf(dj);
-            C[j * (j + 1) / 2 + j] = make_float2(dj, 0.f);
-#pragma unroll
-            for (int r = j + 1; r < K; ++r) {
-                float2 v = C[r * (r + 1) / 2 + j];
-#pragma unroll
-                for (int k = 0; k < j; ++k) v = csub(v, cmulc(C[r * (r + 1) / 2 + k], C[j * (j + 1) / 2 + k]));
-                C[r * (r + 1) / 2 + j] = make_float2(v.x / dj, v.y / dj);
-            }
-        }
-        // Ci = C^-1 (lower), column by column
-        float2 Ci[K * (K + 1) / 2];
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-#pragma unroll
-            for (int r = c; r < K; ++r) {
-                float2 v = make_float2(r == c ? 1.f : 0.f, 0.f);
-#pragma unroll
-                for (int k = c; k < r; ++k) v = csub(v, cmul(C[r * (r + 1) / 2 + k], Ci[k * (k + 1) / 2 + c]));
-                float dr = C[r * (r + 1) / 2 + r].x;
-                Ci[r * (r + 1) / 2 + c] = make_float2(v.x / dr, v.y / dr);
-            }
-        }
+        float2 xo[K];
+        float no_e[K];
+        sb_lmmse::lmmse_diag_solve<K>(Bm, z, xo, no_e);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            // row k of A^-1 = C^-H C^-1: (A^-1)_kj = sum_{r >= max(k, j)} conj(Ci[r, k]) Ci[r, j]
-            float2 gy = make_float2(0.f, 0.f), dd = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                float2 ainv = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int r = (k > j ? k : j); r < K; ++r)
-                    ainv = cadd(ainv, cmulc(Ci[r * (r + 1) / 2 + j], Ci[r * (r + 1) / 2 + k]));
-                gy = cadd(gy, cmul(ainv, z[j]));
-                // B_jk: stored lower triangle, B_jk = conj(B_kj)
-                float2 bjk = j >= k ? Bm[j * (j + 1) / 2 + k] : make_float2(Bm[k * (k + 1) / 2 + j].x, -Bm[k * (k + 1) / 2 + j].y);
-                dd = cadd(dd, cmul(ainv, bjk));
-            }
             if (dp[k] >= 0) {
-                float2 inv = cdiv(make_float2(1.f, 0.f), dd);
-                p.xh[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = cdiv(gy, dd);
-                p.ne[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = inv.x - 1.f;
+                p.xh[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = xo[k];
+                p.ne[(b * p.TXS + ts[k]) * (long long)p.ND + dp[k]] = no_e[k];
             }
         }
     }

@@ -11,6 +11,7 @@
 #include "sb_math.h"
 #include "sb_math2.cuh"
 #include "rng.cuh"
+#include "demap_qam.cuh"
 
 namespace {
 
@@ -208,51 +209,7 @@ __global__ void __launch_bounds__(128) demap_qam_kernel(const float2* __restrict
         if (s < n_sym) {
             const float2 yy = y[s];
             const float inv_n0 = __fdiv_rn(1.0f, fmaxf(no[s / no_inner], tiny));   // one division per symbol
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const float yd = d ? yy.y : yy.x;
-                float e[L];
-#pragma unroll
-                for (int t = 0; t < L; ++t) {
-                    float dd = __fsub_rn(yd, d ? li[t] : lr[t]);
-                    e[t] = __fmul_rn(-__fmul_rn(dd, dd), inv_n0);
-                }
-#pragma unroll
-                for (int u = 0; u < H; ++u) {
-                    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-                    for (int t = 0; t < L; ++t) {
-                        if ((t >> (H - 1 - u)) & 1) mx1 = fmaxf(mx1, e[t]);
-                        else mx0 = fmaxf(mx0, e[t]);
-                    }
-                    float l;
-                    if (METHOD == 1) {
-                        l = __fsub_rn(mx1, mx0);
-                    } else {
-                        mx0 = (mx0 > -INFINITY && mx0 < INFINITY) ? mx0 : 0.f;
-                        mx1 = (mx1 > -INFINITY && mx1 < INFINITY) ? mx1 : 0.f;
-                        float s0 = 0.f, s1 = 0.f;
-                        // the k-th member of group 0 and of group 1 share one packed exp
-#pragma unroll
-                        for (int k = 0; k < L / 2; ++k) {
-                            const int lo = k & ((1 << (H - 1 - u)) - 1), hi = k >> (H - 1 - u);
-                            const int t0 = (hi << (H - u)) | lo, t1 = t0 | (1 << (H - 1 - u));
-                            float a0 = __fsub_rn(e[t0], mx0), a1 = __fsub_rn(e[t1], mx1);
-                            float2 r = sb_expf2_inrange(make_float2(fmaxf(a0, -87.3f), fmaxf(a1, -87.3f)));
-                            if (a0 < -87.3f) r.x = 0.f;
-                            if (a1 < -87.3f) r.y = 0.f;
-                            s0 = __fadd_rn(s0, r.x);
-                            s1 = __fadd_rn(s1, r.y);
-                        }
-                        // both logs in one packed evaluation (sb_logf2 is bit-identical to sb_logf per element)
-                        const float2 lg = sb_logf2(make_float2(fmaxf(s0, 1.17549435e-38f), fmaxf(s1, 1.17549435e-38f)));
-                        float b1 = __fadd_rn(s1 > 0.f ? lg.y : -INFINITY, mx1);
-                        float b0 = __fadd_rn(s0 > 0.f ? lg.x : -INFINITY, mx0);
-                        l = __fsub_rn(b1, b0);
-                    }
-                    out[2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
-                }
-            }
+            demap_qam_symbol<METHOD, H>(yy, inv_n0, lr, li, hard_out, out);
         }
         // stage the warp's 32 x M LLRs through its own shared-memory tile: contiguous global stores, no CTA barrier
         {

@@ -137,8 +137,8 @@ class DecoderStatisticsCallback:
 
     def __call__(self, msg, it, *args, **kwargs):
         # sign of every message with sign(0) := +1, product over the node, all nodes of a codeword positive
-        negative = (msg.flat_values < 0).to(torch.int32)
-        odd = msg.with_flat_values(negative).reduce_sum() % 2                 # parity of the negative signs per node
+        negative = (msg.flat_values < 0).to(torch.float32)
+        odd = msg.with_flat_values(negative).reduce_sum().remainder(2.0)      # parity of the negative signs per node
         cw_success = (odd == 0).all(dim=0)
         self._num_samples[it] += int(msg.flat_values.shape[-1])
         self._decoded_samples[it] += int(cw_success.sum())

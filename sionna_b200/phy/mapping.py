@@ -232,6 +232,25 @@ def _broadcast_inner(t, target_shape, device, dtype, trailing=0):
     return t.expand(tgt).contiguous().reshape(-1), 1
 
 
+def separable_levels_np(p, m):
+    """(levels_re, levels_im) float32 arrays if every point of the 2^m-point constellation ``p`` equals
+    levels_re[even label bits] + 1j * levels_im[odd label bits] exactly (all square QAMs, mapping.py:104-117), else None."""
+    p = np.asarray(p)
+    if m % 2 != 0 or not 2 <= m <= 10:
+        return None
+    h = m // 2
+    j = np.arange(len(p))
+    bits = (j[:, None] >> np.arange(m - 1, -1, -1)) & 1
+    w = 1 << np.arange(h - 1, -1, -1)
+    jr, ji = bits[:, 0::2] @ w, bits[:, 1::2] @ w
+    lev_re, lev_im = np.zeros(1 << h, np.float32), np.zeros(1 << h, np.float32)
+    lev_re[jr[ji == 0]] = p.real[ji == 0]
+    lev_im[ji[jr == 0]] = p.imag[jr == 0]
+    if np.array_equal(lev_re[jr], p.real.astype(np.float32)) and np.array_equal(lev_im[ji], p.imag.astype(np.float32)):
+        return lev_re, lev_im
+    return None
+
+
 class Demapper(Block):
     """Demapper(demapping_method, constellation_type=None, num_bits_per_symbol=None, constellation=None, hard_out=False, precision=None)
 
@@ -286,20 +305,8 @@ class Demapper(Block):
         key = (pts.data_ptr(), pts._version, pts.device)
         if getattr(self, "_sep_key", None) == key:
             return self._sep_val
-        p = pts.detach().cpu().numpy()
-        m = self._constellation.num_bits_per_symbol
-        val = None
-        if m % 2 == 0 and 2 <= m <= 10:
-            h = m // 2
-            j = np.arange(len(p))
-            bits = (j[:, None] >> np.arange(m - 1, -1, -1)) & 1
-            w = 1 << np.arange(h - 1, -1, -1)
-            jr, ji = bits[:, 0::2] @ w, bits[:, 1::2] @ w
-            lev_re, lev_im = np.zeros(1 << h, np.float32), np.zeros(1 << h, np.float32)
-            lev_re[jr[ji == 0]] = p.real[ji == 0]
-            lev_im[ji[jr == 0]] = p.imag[jr == 0]
-            if np.array_equal(lev_re[jr], p.real.astype(np.float32)) and np.array_equal(lev_im[ji], p.imag.astype(np.float32)):
-                val = (torch.from_numpy(lev_re).to(pts.device), torch.from_numpy(lev_im).to(pts.device))
+        lev = separable_levels_np(pts.detach().cpu().numpy(), self._constellation.num_bits_per_symbol)
+        val = None if lev is None else (torch.from_numpy(lev[0]).to(pts.device), torch.from_numpy(lev[1]).to(pts.device))
         self._sep_key, self._sep_val = key, val
         return val
 

@@ -51,15 +51,24 @@ class PUSCHReceiver(Block):
         if stream_management is None:
             stream_management = StreamManagement(np.ones([1, tx._num_tx], bool), tx._num_layers)
         self._stream_management = stream_management
+        self._default_detector = mimo_detector is None
         if mimo_detector is None:
             mimo_detector = LinearDetector("lmmse", "bit", "maxlog", tx.resource_grid, stream_management, "qam",
                                            tx._num_bits_per_symbol, precision=self.precision)
         self._mimo_detector = mimo_detector
+        # default estimator + default detector: one fused launch from the resource grid to the LLRs (ofdm/frontend.py)
+        self._fused = None
+        if channel_estimator is None and self._default_detector and not self._perfect_csi:
+            from ..ofdm.frontend import FusedLSLinearDetector, fusable
+            if fusable(tx.resource_grid, stream_management, self._channel_estimator, mimo_detector._constellation):
+                self._fused = FusedLSLinearDetector(self._channel_estimator, tx.resource_grid, stream_management, "maxlog",
+                                                    constellation=mimo_detector._constellation, precision=self.precision)
         self._layer_demapper = LayerDemapper(tx._layer_mapper, num_bits_per_symbol=tx._num_bits_per_symbol,
                                              precision=self.precision)
         self._tb_decoder = TBDecoder(tx._tb_encoder, precision=self.precision) if tb_decoder is None else tb_decoder
 
     resource_grid = property(lambda self: self._resource_grid)
+    fuse_front_end = True      # set False to run estimator and detector as separate blocks (same numbers up to rounding)
 
     def call(self, y, no, h=None):
         if self._input_domain == "time":
@@ -74,9 +83,11 @@ class PUSCHReceiver(Block):
                 h = self._w.effective_channel(h)
             h_hat = h.contiguous()
             err_var = torch.zeros((), dtype=torch.float32, device=h_hat.device)
+        elif self._fused is not None and self.fuse_front_end:
+            h_hat = None
         else:
             h_hat, err_var = self._channel_estimator(y, no)
-        llr = self._mimo_detector(y, h_hat, err_var, no)
+        llr = self._fused(y, no) if h_hat is None else self._mimo_detector(y, h_hat, err_var, no)
         llr = self._layer_demapper(llr)
         b_hat, tb_crc_status = self._tb_decoder(llr)
         return (b_hat, tb_crc_status) if self._return_tb_crc_status else b_hat

@@ -7,3 +7,4 @@ from .channel_estimation import (BaseChannelEstimator, BaseChannelInterpolator, 
                                  NearestNeighborInterpolator, LinearInterpolator)
 from .equalization import OFDMEqualizer, LMMSEEqualizer
 from .detection import LinearDetector
+from .frontend import FusedLSLinearDetector, fusable, frontend_tables

@@ -287,3 +287,34 @@ def test_stream_management_equals_reference_outputs():
         StreamManagement(np.array([[1, 1], [1, 0]]), 1)
     with pytest.raises(AssertionError):
         StreamManagement(np.array([[2]]), 1)
+
+
+@pytest.mark.parametrize("interp,streams", [("nn", 1), ("lin", 4), ("lin_time_avg", 2)])
+def test_frontend_tables_reproduce_ls_plus_interpolation(interp, streams):
+    """The fused front-end's host tables (ofdm/frontend.py): sum_i t_w * y[t_idx] must equal LS estimation followed by the
+    interpolation (oracle restatement of channel_estimation.py:138-285, 364-734) for random received grids, and e_sum the
+    interpolated, floored error variance per unit noise power summed over the streams."""
+    from sionna_b200.phy.ofdm import ResourceGrid, LSChannelEstimator, frontend_tables
+    from oracle import ofdm as F
+    rg = ResourceGrid(14, 76, 15e3, num_tx=1, num_streams_per_tx=streams, cyclic_prefix_length=6, num_guard_carriers=(5, 6),
+                      dc_null=True, pilot_pattern="kronecker", pilot_ofdm_symbol_indices=[2, 11])
+    est = LSChannelEstimator(rg, interp)
+    t = frontend_tables(rg, est)
+    assert t is not None and t["num_terms"] <= (1 if interp == "nn" else 4)
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=(2, 1, 3, 14, 76)) + 1j * rng.normal(size=(2, 1, 3, 14, 76))
+    eff = F.eff_sc_ind(76, (5, 6), True)
+    mask, pil = rg.pilot_pattern.mask.astype(bool), rg.pilot_pattern.pilots
+    h, err = F.ls_estimate(y[..., eff], mask, pil, 1.0)
+    if interp == "nn":
+        hr, er = F.nn_interp(h, mask, pil), F.nn_interp(err, mask, pil)
+    else:
+        hr, er = F.lin_interp(h, mask, pil, interp == "lin_time_avg"), F.lin_interp(err, mask, pil, interp == "lin_time_avg").real
+    yf = y.reshape(2, 1, 3, -1)
+    idx, w = t["t_idx"], t["t_w"].astype(np.complex128)                      # [ts, RE, NT]
+    got = np.where(idx >= 0, w * yf[..., np.maximum(idx, 0)], 0).sum(-1)     # [B, rx, ant, ts, RE]
+    want = hr.reshape(2, 1, 3, streams, -1)
+    assert np.allclose(got, want, atol=1e-6)
+    e_sum = np.maximum(er[0, 0, 0].reshape(streams, -1), 0).sum(0)
+    assert np.allclose(t["e_sum"], e_sum, rtol=1e-6)
+    assert np.array_equal(t["re_full"], (np.arange(14)[:, None] * 76 + eff[None, :]).reshape(-1))

@@ -249,3 +249,48 @@ def test_signal_fft_ifft(cuda_device):
     y = _c64(rng, (7, 100))
     np.testing.assert_allclose(ifft(torch.from_numpy(y).to(cuda_device)).cpu().numpy(),
                                np.fft.ifft(y.astype(complex)) * 10.0, atol=2e-5)
+
+
+@pytest.mark.parametrize("cfg", ["siso_nn_64qam", "mimo4x16_lin_16qam", "mimo2x8_linavg_qpsk", "mimo3x8_nn_256qam"])
+def test_fused_front_end_equals_the_separate_blocks(cuda_device, cfg):
+    """sb_ofdm_frontend (one launch: LS + interpolation + LMMSE + demapping from host-built linear tables) against the
+    chain LSChannelEstimator -> LMMSEEqualizer / LinearDetector it replaces, on identical received grids: x_hat, no_eff
+    and LLRs agree to fp32 rounding (the fused kernel forms h_hat as one weighted sum instead of two interpolation passes)."""
+    from sionna_b200.phy.ofdm import (LSChannelEstimator, LMMSEEqualizer, LinearDetector, ResourceGridMapper,
+                                      FusedLSLinearDetector, fusable)
+    from sionna_b200.phy.mimo import StreamManagement
+    from sionna_b200.phy.mapping import Constellation
+    from sionna_b200.phy.channel import ApplyOFDMChannel
+    streams, ant, interp, mbits, method = {"siso_nn_64qam": (1, 1, "nn", 6, "app"), "mimo4x16_lin_16qam": (4, 16, "lin", 4, "app"),
+                                           "mimo2x8_linavg_qpsk": (2, 8, "lin_time_avg", 2, "maxlog"),
+                                           "mimo3x8_nn_256qam": (3, 8, "nn", 8, "maxlog")}[cfg]
+    rng = np.random.default_rng(42)
+    rg = _grid(1, streams)
+    sm = StreamManagement(np.array([[1]]), streams)
+    b = 5
+    pts = M.qam(mbits)
+    xd = pts[rng.integers(0, len(pts), (b, 1, streams, rg.num_data_symbols))]
+    grid = ResourceGridMapper(rg)(torch.from_numpy(xd).to(cuda_device))
+    h = _c64(rng, (b, 1, ant, 1, streams, 14, 1)) * np.exp(2j * np.pi * 0.004 * np.arange(76)).reshape(1, 1, 1, 1, 1, 1, 76) \
+        + 0.05 * _c64(rng, (b, 1, ant, 1, streams, 14, 76))
+    no = torch.from_numpy(rng.uniform(0.01, 0.03, size=(b, 1, ant)).astype(np.float32)).to(cuda_device)
+    y = ApplyOFDMChannel()(grid, torch.from_numpy(h.astype(np.complex64)).to(cuda_device), no)
+    est = LSChannelEstimator(rg, interp)
+    assert fusable(rg, sm, est, Constellation("qam", mbits))
+    h_hat, ev = est(y, no)
+    x_ref, n_ref = LMMSEEqualizer(rg, sm)(y, h_hat, ev, no)
+    llr_ref = LinearDetector("lmmse", "bit", method, rg, sm, "qam", mbits)(y, h_hat, ev, no)
+    fused = FusedLSLinearDetector(est, rg, sm, method, "qam", mbits)
+    x_f, n_f = fused.equalize(y, no)
+    llr_f = fused(y, no)
+    assert x_f.shape == x_ref.shape and llr_f.shape == llr_ref.shape
+    np.testing.assert_allclose(x_f.cpu().numpy(), x_ref.cpu().numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(n_f.cpu().numpy(), n_ref.cpu().numpy(), rtol=2e-4, atol=1e-6)
+    scale = float(llr_ref.abs().max())
+    assert float((llr_f - llr_ref).abs().max()) <= 2e-4 * scale
+    hard = FusedLSLinearDetector(est, rg, sm, method, "qam", mbits, hard_out=True)(y, no)
+    sure = llr_ref.abs() > 1e-3 * scale
+    assert torch.equal(hard[sure], (llr_ref[sure] > 0).float())
+    # not fusable: interfering streams
+    sm2 = StreamManagement(np.array([[1, 0], [0, 1]]), 1)
+    assert not fusable(_grid(2, 1), sm2, LSChannelEstimator(_grid(2, 1), "nn"), None)

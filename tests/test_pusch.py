@@ -448,3 +448,57 @@ def test_pusch_estimator_sweep_block_constant_channel():
     for cfg in ((1, 1, 0, 1, 2), (2, 2, 1, 2, 3), (4, 1, 2, 1, 2)):
         want, h_hat, e_hat = _pusch_estimation_case(*cfg, rng, no=0.01)
         assert abs(np.var(want - h_hat) - e_hat.mean()) < 1e-2 and abs(np.var(want - h_hat) / e_hat.mean() - 1) < 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["2layers_8ant_lin", "1layer_4ant_double_symbol", "4layers_nn"])
+def test_pusch_receiver_fused_front_end_equals_separate_blocks(cuda_device, cfg):
+    """PUSCHReceiver's default front-end runs as ONE launch (PUSCHLSChannelEstimator incl. CDM de-spreading + linear
+    interpolation + LMMSE + max-log demapping, ofdm/frontend.py). Switching the fusion off runs the three blocks of the
+    reference's receiver one after the other: same LLRs to fp32 rounding, same decoded transport blocks."""
+    import torch
+    from sionna_b200.phy.nr import PUSCHConfig, PUSCHTransmitter, PUSCHReceiver
+    from sionna_b200.phy.nr.pusch_channel_estimation import PUSCHLSChannelEstimator
+    from sionna_b200.phy.channel import ApplyOFDMChannel, TDL, subcarrier_frequencies, cir_to_ofdm_channel
+    from sionna_b200.phy import config
+    config.seed = 77
+    if cfg == "2layers_8ant_lin":
+        pc, ant = PUSCHConfig(num_layers=2, num_antenna_ports=2), 8
+        pc.dmrs.additional_position = 1
+    elif cfg == "1layer_4ant_double_symbol":
+        pc, ant = PUSCHConfig(), 4
+        pc.dmrs.length = 2
+        pc.dmrs.additional_position = 1
+    else:
+        pc, ant = PUSCHConfig(num_layers=4, num_antenna_ports=4), 16
+        pc.dmrs.config_type = 2
+        pc.dmrs.num_cdm_groups_without_data = 2
+    pc.carrier.n_size_grid = 6
+    pc.tb.mcs_index = 12
+    tx = PUSCHTransmitter(pc)
+    rx = PUSCHReceiver(tx)
+    if cfg == "4layers_nn":
+        est = PUSCHLSChannelEstimator(tx.resource_grid, tx._dmrs_length, tx._dmrs_additional_position,
+                                      tx._num_cdm_groups_without_data, interpolation_type="nn")
+        rx = PUSCHReceiver(tx)
+        from sionna_b200.phy.ofdm.frontend import FusedLSLinearDetector
+        rx._channel_estimator = est
+        rx._fused = FusedLSLinearDetector(est, tx.resource_grid, rx._stream_management, "maxlog",
+                                          constellation=rx._mimo_detector._constellation)
+    assert rx._fused is not None
+    rg = tx.resource_grid
+    x, b = tx(32)
+    a, tau = TDL("B", 100e-9, 3.5e9, min_speed=3.0, num_rx_ant=ant, num_tx_ant=pc.num_antenna_ports)(32, rg.num_ofdm_symbols,
+                                                                                           1.0 / rg.ofdm_symbol_duration)
+    h = cir_to_ofdm_channel(subcarrier_frequencies(rg.fft_size, rg.subcarrier_spacing), a, tau, normalize=True)
+    no = 0.02
+    y = ApplyOFDMChannel()(x, h, no)
+    llr_f = rx._fused(y, no)
+    h_hat, ev = rx._channel_estimator(y, no)
+    llr_u = rx._mimo_detector(y, h_hat, ev, no)
+    scale = float(llr_u.abs().max())
+    assert llr_f.shape == llr_u.shape and float((llr_f - llr_u).abs().max()) <= 3e-4 * scale
+    b_f = rx(y, no)
+    rx.fuse_front_end = False
+    b_u = rx(y, no)
+    assert torch.equal(b_f, b_u) and float((b_f != b).float().mean()) < 1e-3

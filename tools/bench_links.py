@@ -146,6 +146,8 @@ class OfdmSiso(Workload):
         self.demod = OFDMDemodulator(rg.fft_size, l_min, rg.cyclic_prefix_length)
         self.est, self.eq = LSChannelEstimator(rg, "nn"), LMMSEEqualizer(rg, sm)
         self.demapper = Demapper("app", "qam", m)
+        from sionna_b200.phy.ofdm import FusedLSLinearDetector
+        self.fused = FusedLSLinearDetector(self.est, rg, sm, "app", "qam", m)       # one launch: LS + nn + LMMSE + demap
         nd = rg.num_data_symbols
         for _ in range(2):
             b = src([self.batch, 1, 1, nd * m])
@@ -157,6 +159,10 @@ class OfdmSiso(Workload):
 
     def run(self, i, x=None):
         y = self.demod(self.inputs[i & 1] if x is None else x)
+        return self.fused(y, self.no)
+
+    def run_separate(self, i):
+        y = self.demod(self.inputs[i & 1])
         h_hat, ev = self.est(y, self.no)
         x_hat, no_eff = self.eq(y, h_hat, ev, self.no)
         return self.demapper(x_hat, no_eff)
@@ -170,11 +176,13 @@ class OfdmSiso(Workload):
         nsamp, n_re, nd, f_eff = yt.shape[-1], 14 * 76, rg.num_data_symbols, rg.num_effective_subcarriers
         return [
             ("OFDMDemodulator 76-pt", lambda: self.demod(yt), b * (nsamp + n_re) * 8, "16 B per sample in + out"),
-            ("LSChannelEstimator nn", lambda: self.est(y, self.no), b * (n_re * 8 + 14 * f_eff * 12),
+            ("Fused LS(nn)+LMMSE+demap (sb_ofdm_frontend)", lambda: self.fused(y, self.no), b * (n_re * 8 + nd * 24),
+             "full grid y in, 6 LLRs per data RE out; nothing else touches HBM"),
+            ("[separate] LSChannelEstimator nn", lambda: self.est(y, self.no), b * (n_re * 8 + 14 * f_eff * 12),
              "y in; h_hat c64 + err_var f32 out"),
-            ("LMMSEEqualizer 1x1", lambda: self.eq(y, h_hat, ev, self.no), b * (14 * f_eff * (8 + 8 + 4) + nd * 12),
+            ("[separate] LMMSEEqualizer 1x1", lambda: self.eq(y, h_hat, ev, self.no), b * (14 * f_eff * (8 + 8 + 4) + nd * 12),
              "y + h_hat + err_var in, x_hat + no_eff out"),
-            ("Demapper app 64-QAM", lambda: self.demapper(x_hat, no_eff), b * nd * (8 + 4 + 24), "x_hat + no_eff in, 6 LLRs out"),
+            ("[separate] Demapper app 64-QAM", lambda: self.demapper(x_hat, no_eff), b * nd * (8 + 4 + 24), "x_hat + no_eff in, 6 LLRs out"),
         ]
 
     def cpu_chain(self, n):
@@ -224,6 +232,8 @@ class MimoOfdm(Workload):
         freqs, chan = subcarrier_frequencies(76, 15e3), ApplyOFDMChannel()
         self.est = LSChannelEstimator(rg, "nn")
         self.det = LinearDetector("lmmse", "bit", "app", rg, sm, "qam", self.m)
+        from sionna_b200.phy.ofdm import FusedLSLinearDetector
+        self.fused = FusedLSLinearDetector(self.est, rg, sm, "app", "qam", self.m)
         self.counter = ErrorCounter(self.dev)
         for _ in range(2):
             b = src([self.batch, 1, self.streams, self.k])
@@ -237,8 +247,7 @@ class MimoOfdm(Workload):
 
     def run(self, i, x=None):
         y = self.inputs[i & 1] if x is None else x
-        h_hat, ev = self.est(y, self.no)
-        llr = self.det(y, h_hat, ev, self.no)
+        llr = self.fused(y, self.no)
         b_hat = self.dec(llr)
         if x is None:
             self.counter.update(self.truth[i & 1], b_hat)
@@ -252,9 +261,11 @@ class MimoOfdm(Workload):
         n_re = b * 14 * f_eff
         e, nv = self.dec.num_edges, self.dec.num_vns
         return [
-            ("LSChannelEstimator nn 4x16", lambda: self.est(y, self.no), b * M * 14 * 76 * 8 + b * M * K * 14 * f_eff * 12,
+            ("Fused LS(nn)+LMMSE+demap 4x16 (sb_ofdm_frontend)", lambda: self.fused(y, self.no),
+             b * (M * 14 * 76 * 8 + K * nd * self.m * 4), "full grid y (16 antennas) in, LLRs out"),
+            ("[separate] LSChannelEstimator nn 4x16", lambda: self.est(y, self.no), b * M * 14 * 76 * 8 + b * M * K * 14 * f_eff * 12,
              "y in; h_hat c64 + err_var f32 out over the grid"),
-            ("LinearDetector lmmse/app 16-QAM", lambda: self.det(y, h_hat, ev, self.no),
+            ("[separate] LinearDetector lmmse/app 16-QAM", lambda: self.det(y, h_hat, ev, self.no),
              n_re * (M * 8 + M * K * 8 + 4) + b * K * nd * self.m * 4,
              "SURVEY 8d: y 128 B + H 512 B + no 4 B per RE in; LLRs out (x_hat / no_eff stay internal to the detector)"),
             ("LDPC5GDecoder BP-20", lambda: self.dec(llr), b * K * (20 * (8 * e + 4 * nv) + 4 * self.n + 4 * self.k),
@@ -353,9 +364,11 @@ class Pusch(Workload):
         cbs = rx._tb_decoder._num_cbs
         e, nv, n_cb, k_cb = dec.num_edges, dec.num_vns, dec.encoder.n, dec.encoder.k
         return [
-            ("PUSCHLSChannelEstimator lin", lambda: rx._channel_estimator(y, self.no),
+            ("Fused PUSCH LS+CDM+lin+LMMSE+demap (sb_ofdm_frontend)", lambda: rx._fused(y, self.no),
+             b * (ant * rg.num_ofdm_symbols * rg.fft_size * 8 + lay * nd * m * 4), "full grid y in, LLRs out"),
+            ("[separate] PUSCHLSChannelEstimator lin", lambda: rx._channel_estimator(y, self.no),
              n_re * ant * 8 + n_re * ant * lay * 12, "y in; h_hat c64 + err_var f32 out over the grid"),
-            ("LinearDetector lmmse/maxlog", lambda: rx._mimo_detector(y, h_hat, ev, self.no),
+            ("[separate] LinearDetector lmmse/maxlog", lambda: rx._mimo_detector(y, h_hat, ev, self.no),
              n_re * (ant * 8 + ant * lay * 8 + ant * lay * 4 + 4) + b * lay * nd * m * 4,
              "per RE: y + H + err_var + no in; LLRs out"),
             ("LayerDemapper + TBDecoder BP-20", lambda: rx._tb_decoder(rx._layer_demapper(llr)),
