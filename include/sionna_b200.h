@@ -117,6 +117,15 @@ int sb_ldpc_decode(const sb_ldpc_graph* g, const float* d_llr, int64_t batch, in
                    const float* d_state_in, float* d_state_out, float* d_out,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Same decode with opt-in EARLY TERMINATION (the reference always runs num_iter iterations,
+ * decoding.py:105-107): a codeword stops as soon as every check node is satisfied by the signs of its incoming messages
+ * (the criterion of the reference's DecoderStatisticsCallback, ldpc/utils.py:131-140), at most max_iter iterations.
+ * d_num_iter [batch] (optional) receives the iterations run per codeword; the outputs of a codeword equal those of
+ * sb_ldpc_decode with num_iter = d_num_iter[b] bit for bit. Only for graphs on the quasi-cyclic on-chip path (flooding,
+ * "sum" VN rule); SB_EUNSUPPORTED otherwise. */
+int sb_ldpc_decode_early(const sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_t max_iter, int32_t cn_rule,
+                         float offset, float llr_max, int32_t hard_out, float* d_out, int32_t* d_num_iter, void* stream);
+
 /* Unfused belief propagation (csrc/ldpc_bp_flat.cu): one call per half-iteration on [num_edges, batch] message tensors
  * in the reference's layouts, for decoders with Python callbacks (`v2c_callbacks` / `c2v_callbacks`, decoding.py:484-486,
  * 513-515) or user-supplied node updates. msg_v2c is in VN order (edge e of decoding.py:286-288), msg_c2v in CN-view

@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_ldpc_graph_on_chip": (i32, [vp]),
     "sb_ldpc_workspace_bytes": (sz, [vp]),
     "sb_ldpc_decode": (i32, [vp, vp, i64, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "sb_ldpc_decode_early": (i32, [vp, vp, i64, i32, i32, f32, f32, i32, vp, vp, vp]),
     "sb_ldpc_flat_init": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "sb_ldpc_flat_cn": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, vp]),
     "sb_ldpc_flat_vn": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp]),

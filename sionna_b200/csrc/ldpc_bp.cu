@@ -455,10 +455,30 @@ static int launch_bp(const sb_ldpc_graph* g, const BpParams& p, int threads, siz
     return SB_OK;
 }
 
+static int ldpc_decode_impl(const sb_ldpc_graph* gc, const float* d_llr, int64_t batch, int32_t num_iter, int32_t cn_rule,
+                            int32_t vn_rule, float offset, float llr_max, int32_t hard_out, const float* d_state_in,
+                            float* d_state_out, float* d_out, void* d_ws, size_t ws_bytes, void* stream, int32_t early,
+                            int32_t* d_iters);
+
 extern "C" int sb_ldpc_decode(const sb_ldpc_graph* gc, const float* d_llr, int64_t batch, int32_t num_iter,
                               int32_t cn_rule, int32_t vn_rule, float offset, float llr_max, int32_t hard_out,
                               const float* d_state_in, float* d_state_out, float* d_out, void* d_ws,
                               size_t ws_bytes, void* stream) {
+    return ldpc_decode_impl(gc, d_llr, batch, num_iter, cn_rule, vn_rule, offset, llr_max, hard_out, d_state_in, d_state_out,
+                            d_out, d_ws, ws_bytes, stream, 0, nullptr);
+}
+
+extern "C" int sb_ldpc_decode_early(const sb_ldpc_graph* gc, const float* d_llr, int64_t batch, int32_t max_iter,
+                                    int32_t cn_rule, float offset, float llr_max, int32_t hard_out, float* d_out,
+                                    int32_t* d_num_iter, void* stream) {
+    return ldpc_decode_impl(gc, d_llr, batch, max_iter, cn_rule, SB_VN_SUM, offset, llr_max, hard_out, nullptr, nullptr, d_out,
+                            nullptr, 0, stream, 1, d_num_iter);
+}
+
+static int ldpc_decode_impl(const sb_ldpc_graph* gc, const float* d_llr, int64_t batch, int32_t num_iter, int32_t cn_rule,
+                            int32_t vn_rule, float offset, float llr_max, int32_t hard_out, const float* d_state_in,
+                            float* d_state_out, float* d_out, void* d_ws, size_t ws_bytes, void* stream, int32_t early,
+                            int32_t* d_iters) {
     if (batch == 0) return SB_OK;                         // empty batch: nothing to do, pointers may be null
     SB_CHECK_ARG(gc && d_llr && d_out, "sb_ldpc_decode: null graph/input/output");
     SB_CHECK_ARG(batch >= 0 && num_iter >= 0, "sb_ldpc_decode: negative batch or num_iter");
@@ -472,8 +492,12 @@ extern "C" int sb_ldpc_decode(const sb_ldpc_graph* gc, const float* d_llr, int64
     {   // quasi-cyclic fast path (ldpc_bp_qc.cu) when the graph carries a QC description and the call qualifies
         bool handled = false;
         rc = sb_qc_try_decode(g, d_llr, batch, num_iter, cn_rule, vn_rule, offset, llr_max, hard_out, d_state_in,
-                              d_state_out, d_out, (cudaStream_t)stream, &handled);
+                              d_state_out, d_out, (cudaStream_t)stream, &handled, early, d_iters);
         if (rc || handled) return rc;
+    }
+    if (early) {
+        sb_set_error("sb_ldpc_decode_early: early termination needs the quasi-cyclic on-chip path (5G codes, flooding)");
+        return SB_EUNSUPPORTED;
     }
     const bool on_chip = graph_on_chip(g, g->smem_optin);
     BpParams p{};

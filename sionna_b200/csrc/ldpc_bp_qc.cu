@@ -45,6 +45,8 @@ struct QcParams {
     float* state_out;
     long long B;
     int num_iter, hard_out, use_tma;
+    int early;               // opt-in early termination: stop once every check node is satisfied (see the kernel)
+    int* iters_out;          // [B] iterations actually run per codeword, or nullptr
     int tab_rep;             // copies of the phi log table in shared memory (32, 8 or 1; 0: rule does not use it)
     float offset, llr_max;
 };
@@ -75,7 +77,7 @@ struct QcParams {
 // which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
 template <bool SC, class LT>
 __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
-                                          const LT& lt) {
+                                          const LT& lt, int* unsat) {
     const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
@@ -110,6 +112,7 @@ SB_UNROLL(SB_PHI_UNROLL)
         *q0 = __uint_as_float(__float_as_uint(p) | (b0 & 0x80000000u));
     }
     par &= 0x80000000u;
+    if (unsat && par) *unsat = 1;                         // early termination: this check is not satisfied
     float yP = 0.f;                                       // phi(P), evaluated lazily (2)
     bool have_yP = false;
     l = 0;
@@ -147,9 +150,14 @@ SB_UNROLL(SB_PHI_UNROLL)
     }
 }
 
-__device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip) {
+__device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip, int* unsat) {
     const float atanh_clip = (float)(1 - 1e-7);
     float prod = 1.f;
+    if (unsat) {                                          // sign product of the incoming messages (sign(0) := +1)
+        unsigned par = 0;
+        for (int l = 0; l < deg; ++l) par ^= __float_as_uint(pm[l * Z]);
+        if (par & 0x80000000u) *unsat = 1;
+    }
 #pragma unroll 2
     for (int l = 0; l < deg; ++l) {
         float* q = pm + l * Z;
@@ -173,7 +181,7 @@ __device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip
 //   unique minimum -> that edge gets fl(fl(m2 - m1) + m1), all others m1;  repeated minimum -> all edges m1.
 // Offset, max(.,0) and clipping act on only two distinct magnitudes and are hoisted out of the edge loop.
 template <int DMAX, bool EXACT>                           // EXACT: deg == DMAX, no per-edge guards
-__device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset) {
+__device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset, int* unsat) {
     float x[DMAX];                                        // every element is assigned unconditionally (registers)
     float m1 = INFINITY, m2 = INFINITY;
     unsigned par = 0;
@@ -188,6 +196,7 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
         par ^= __float_as_uint(v);
     }
     par &= 0x80000000u;
+    if (unsat && par) *unsat = 1;
     float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
     if (deg == 1) min_e = __fadd_rn(100000.f, m1);
     const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
@@ -202,7 +211,7 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
 }
 
 // generic-degree fallback (re-reads shared memory instead of holding the row in registers)
-__device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, float clip, float offset) {
+__device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, float clip, float offset, int* unsat) {
     float m1 = INFINITY, m2 = INFINITY;
     unsigned par = 0;
     for (int l = 0; l < deg; ++l) {
@@ -213,6 +222,7 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
         par ^= __float_as_uint(v);
     }
     par &= 0x80000000u;
+    if (unsat && par) *unsat = 1;
     float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
     if (deg == 1) min_e = __fadd_rn(100000.f, m1);
     const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
@@ -226,32 +236,32 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
 
 template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset, float phi_max, bool sc,
-                                      int* sat_flag, const LT& lt) {
+                                      int* sat_flag, const LT& lt, int* unsat) {
     if (RULE == SB_CN_BOXPLUS_PHI) {
-        if (sc) cn_phi_qc<true, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
-        else cn_phi_qc<false, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
+        if (sc) cn_phi_qc<true, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt, unsat);
+        else cn_phi_qc<false, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt, unsat);
     }
-    else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
+    else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip, unsat);
     else {
         const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
         // exact-degree code for the degrees of the 5G base graphs, guarded buckets otherwise (deg is warp-uniform)
         if (CLS == 4) {
-            if (deg == 3) cn_minsum_qc<3, true>(pm, Z, deg, clip, off);
-            else if (deg == 4) cn_minsum_qc<4, true>(pm, Z, deg, clip, off);
-            else cn_minsum_qc<4, false>(pm, Z, deg, clip, off);
+            if (deg == 3) cn_minsum_qc<3, true>(pm, Z, deg, clip, off, unsat);
+            else if (deg == 4) cn_minsum_qc<4, true>(pm, Z, deg, clip, off, unsat);
+            else cn_minsum_qc<4, false>(pm, Z, deg, clip, off, unsat);
         } else if (CLS == 3) {
-            if (deg == 5) cn_minsum_qc<5, true>(pm, Z, deg, clip, off);
-            else if (deg == 6) cn_minsum_qc<6, true>(pm, Z, deg, clip, off);
-            else if (deg == 7) cn_minsum_qc<7, true>(pm, Z, deg, clip, off);
-            else cn_minsum_qc<8, true>(pm, Z, deg, clip, off);
+            if (deg == 5) cn_minsum_qc<5, true>(pm, Z, deg, clip, off, unsat);
+            else if (deg == 6) cn_minsum_qc<6, true>(pm, Z, deg, clip, off, unsat);
+            else if (deg == 7) cn_minsum_qc<7, true>(pm, Z, deg, clip, off, unsat);
+            else cn_minsum_qc<8, true>(pm, Z, deg, clip, off, unsat);
         } else if (CLS == 2) {
-            if (deg == 9) cn_minsum_qc<9, true>(pm, Z, deg, clip, off);
-            else if (deg == 10) cn_minsum_qc<10, true>(pm, Z, deg, clip, off);
-            else cn_minsum_qc<12, false>(pm, Z, deg, clip, off);
+            if (deg == 9) cn_minsum_qc<9, true>(pm, Z, deg, clip, off, unsat);
+            else if (deg == 10) cn_minsum_qc<10, true>(pm, Z, deg, clip, off, unsat);
+            else cn_minsum_qc<12, false>(pm, Z, deg, clip, off, unsat);
         } else if (CLS == 1) {
-            if (deg == 19) cn_minsum_qc<19, true>(pm, Z, deg, clip, off);
-            else cn_minsum_qc<20, false>(pm, Z, deg, clip, off);
-        } else cn_minsum_qc_loop(pm, Z, deg, clip, off);
+            if (deg == 19) cn_minsum_qc<19, true>(pm, Z, deg, clip, off, unsat);
+            else cn_minsum_qc<20, false>(pm, Z, deg, clip, off, unsat);
+        } else cn_minsum_qc_loop(pm, Z, deg, clip, off, unsat);
     }
 }
 
@@ -384,12 +394,12 @@ __device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx&
 template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
                                          const int4* s_row, int start, int end, float clip, bool fuse,
-                                         float phi_max, bool sc, int* sat_flag, const LT& lt) {
+                                         float phi_max, bool sc, int* sat_flag, const LT& lt, int* unsat) {
     for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
         int4 ri = s_row[rr];
         if (w.lane_i < ri.z) {
             float* pm = msg + ri.x * p.Z + w.lane_i;
-            cn_qc<RULE, CLS, LT>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt);
+            cn_qc<RULE, CLS, LT>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt, unsat);
             if (fuse && ri.w >= 0) {
                 // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
                 // with a single incoming message) so the VN phase can skip the column
@@ -466,7 +476,8 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
     int2* s_ce_p = reinterpret_cast<int2*>(smem_raw + off_ce);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
     int* sat_flag = reinterpret_cast<int*>(smem_raw + off_bar + 8);
-    const int off_tab = off_bar + 16;                     // phi log table, tab_rep copies interleaved per entry
+    int* unsat2 = reinterpret_cast<int*>(smem_raw + off_bar + 16);   // [2] "some check is unsatisfied", alternating per iteration
+    const int off_tab = off_bar + 32;                     // phi log table, tab_rep copies interleaved per entry
     const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
     const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
             }
         }
         __syncthreads();
-        if (tid == 0) *sat_flag = 0;
+        if (tid == 0) { *sat_flag = 0; unsat2[0] = 0; unsat2[1] = 0; }
         // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
         vn_all<1, true>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
         __syncthreads();
@@ -537,24 +548,36 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
                 }
             }
         }
-        for (int it = 0; it < p.num_iter; ++it) {
-            const bool final_pass = it == p.num_iter - 1;
+        // Early termination (opt-in, the reference has none: decoding.py:105-107): a codeword stops once every check node
+        // is satisfied by the signs of its incoming messages (the convergence criterion of the reference's
+        // DecoderStatisticsCallback, ldpc/utils.py:131-140). The CN phase of iteration `it` reports unsatisfied checks in
+        // unsat2[it & 1]; when none was reported the NEXT iteration becomes the final one (its CN phase must not fuse
+        // the degree-1 updates), so the outputs equal a fixed-iteration decode with num_iter = `limit` bit for bit.
+        int limit = p.num_iter;
+        for (int it = 0; it < limit; ++it) {
+            const bool final_pass = it == limit - 1;
+            int* unsat = p.early ? unsat2 + (it & 1) : nullptr;
             const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
             if (final_pass && tid == 0 && p.use_tma && b + gridDim.x < p.B)   // pull the next codeword's logits into L2 early
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.llr + (size_t)(b + gridDim.x) * p.n_in),
                              "r"((uint32_t)p.n_in * 4u) : "memory");
             const int* re = p.row_cls_end;
-            cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 2, LogTab<REP>>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 3, LogTab<REP>>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt);
-            cn_class<RULE, 4, LogTab<REP>>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt);
+            cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
+            cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
+            cn_class<RULE, 2, LogTab<REP>>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
+            cn_class<RULE, 3, LogTab<REP>>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
+            cn_class<RULE, 4, LogTab<REP>>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
             __syncthreads();
+            if (p.early) {
+                if (!final_pass && unsat2[it & 1] == 0) limit = it + 2;        // CTA-uniform (read between two barriers)
+                if (tid == 0) unsat2[(it + 1) & 1] = 0;                       // the other slot is idle until the next CN phase
+            }
             // ---- VN phase ---------------------------------------------------------------------------------------
             vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
             __syncthreads();
         }
+        if (p.iters_out && tid == 0) p.iters_out[b] = limit;
         if (p.state_out) {
             float* st = p.state_out + (size_t)b * p.E;
             for (int e = tid; e < p.E; e += T) st[e] = __fmul_rn(msg[p.slot_of_edge[e]], -1.f);
@@ -565,7 +588,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
 
 size_t qc_smem_bytes(const sb_ldpc_graph* g, int tab_rep) {
     return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 16 +
-           (size_t)g->qc_nnz * 8 + 16 + 16 + (size_t)tab_rep * SB_LOGTAB_N * 8;
+           (size_t)g->qc_nnz * 8 + 16 + 32 + (size_t)tab_rep * SB_LOGTAB_N * 8;
 }
 
 template <typename T>
@@ -802,7 +825,7 @@ extern "C" int sb_ldpc_graph_is_qc(const sb_ldpc_graph* g) { return g && g->qc ?
 
 int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_t num_iter, int32_t cn_rule,
                      int32_t vn_rule, float offset, float llr_max, int32_t hard_out, const float* d_state_in,
-                     float* d_state_out, float* d_out, cudaStream_t stream, bool* handled) {
+                     float* d_state_out, float* d_out, cudaStream_t stream, bool* handled, int32_t early, int32_t* d_iters) {
     *handled = false;
     if (!g->qc || !g->flooding || vn_rule != SB_VN_SUM || d_state_in || cn_rule > SB_CN_OFFSET_MINSUM) return SB_OK;
     // boxplus-phi keeps the log table of phi in shared memory: one copy per bank pair if it fits, else a single copy
@@ -826,6 +849,7 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     p.slot_of_edge = g->d_qc_slot_of_edge;
     p.llr = d_llr; p.out = d_out; p.state_out = d_state_out; p.B = batch; p.num_iter = num_iter; p.hard_out = hard_out;
     p.offset = offset; p.llr_max = llr_max; p.tab_rep = tab_rep;
+    p.early = early; p.iters_out = d_iters;
     p.use_tma = (g->n_in % 4 == 0) && (g->n_in <= p.E_alloc) && ((reinterpret_cast<uintptr_t>(d_llr) & 15) == 0);
     const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
     const int max_warps = qc_max_threads(cn_rule) / 32;

@@ -39,7 +39,8 @@ static const int kSmemOptinB200 = 232448;
 // ldpc_bp_qc.cu: runs the QC kernel if the graph / call qualifies; *handled tells the dispatcher.
 int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_t num_iter, int32_t cn_rule,
                      int32_t vn_rule, float offset, float llr_max, int32_t hard_out, const float* d_state_in,
-                     float* d_state_out, float* d_out, cudaStream_t stream, bool* handled);
+                     float* d_state_out, float* d_out, cudaStream_t stream, bool* handled, int32_t early = 0,
+                     int32_t* d_iters = nullptr);
 void sb_qc_free_device(sb_ldpc_graph* g);
 
 #if defined(__CUDACC__)

@@ -114,6 +114,11 @@ class LDPCBPDecoder(Block):
     ragged tensor): such decoders run the unfused path - one kernel launch per half-iteration on ``[num_edges, batch]``
     tensors in the reference's layouts and list orders - instead of the fused shared-memory kernels.
 
+    Extension (keyword ``early_stop=True``, not in the reference, 5G / quasi-cyclic codes only): every codeword stops
+    as soon as all its check nodes are satisfied instead of always running ``num_iter`` iterations
+    (decoding.py:105-107); ``decoder.num_iter_run`` then holds the iterations each codeword of the last call ran, and
+    its output equals a fixed ``num_iter_run``-iteration decode bit for bit. Off by default.
+
     Extension (keyword ``sum_order``, not in the reference): ``"ascending"`` (default) combines the messages of a node
     in ascending neighbour index, which the quasi-cyclic fast path needs; ``"reference"`` walks them in the reference's
     own list orders (``np.argsort`` results of decoding.py:286, 329) on the generic kernel. fp32 sums depend on their
@@ -126,6 +131,8 @@ class LDPCBPDecoder(Block):
                  precision=None, **kwargs):
         if "cn_type" in kwargs:
             raise TypeError("'cn_type' is deprecated; use 'cn_update' instead.")
+        self._early_stop = bool(kwargs.pop("early_stop", False))
+        self.num_iter_run = None                            # [batch] int32: iterations per codeword of the last call
         sum_order = kwargs.pop("sum_order", "ascending")
         if sum_order not in ("ascending", "reference"):
             raise ValueError("sum_order must be 'ascending' or 'reference'.")
@@ -394,11 +401,28 @@ class LDPCBPDecoder(Block):
                                  int(self._hard_out), st), "sb_ldpc_flat_out")
         return out, st_out
 
+    def _decode_early(self, llr2d, num_iter, msg_v2c):
+        """``early_stop=True``: at most ``num_iter`` iterations, every codeword stops once all its check nodes are
+        satisfied (``sb_ldpc_decode_early``); ``self.num_iter_run`` holds the iterations each codeword ran."""
+        if msg_v2c is not None or self._return_state:
+            raise ValueError("early_stop cannot be combined with a decoder state (msg_v2c / return_state)")
+        if self._vn_rule != _VN_RULES["sum"] or self._cn_rule == _CN_RULES["identity"]:
+            raise ValueError("early_stop needs a check-node rule and the 'sum' variable-node rule")
+        g, dev, b = self._graph, llr2d.device, llr2d.shape[0]
+        out = torch.empty((b, g.n_out), dtype=torch.float32, device=dev)
+        self.num_iter_run = torch.empty(b, dtype=torch.int32, device=dev)
+        check(lib().sb_ldpc_decode_early(g.handle, ptr(llr2d), b, int(num_iter), self._cn_rule, self._offset, self._llr_max,
+                                         int(self._hard_out), ptr(out), ptr(self.num_iter_run), current_stream()),
+              "sb_ldpc_decode_early")
+        return out, None
+
     def _decode(self, llr2d, num_iter, msg_v2c):
         if self.precision != "single":
             raise NotImplementedError("sb_ldpc_decode is an fp32 kernel; precision='double' is not available.")
         if self._unfused:
             return self._decode_unfused(llr2d, num_iter, msg_v2c)
+        if self._early_stop:
+            return self._decode_early(llr2d, num_iter, msg_v2c)
         g = self._graph
         dev = llr2d.device
         b = llr2d.shape[0]

@@ -314,3 +314,34 @@ def test_full_batch_4096_bit_exact_vs_oracle(cuda_device, rule):
         x2 = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20, sum_order="reference")(
             torch.from_numpy(llr).to(cuda_device)).cpu().numpy()
         assert np.array_equal(x2, ref(llr, math_mode=0, order="reference", num_threads=threads, pure=True))
+
+
+@pytest.mark.parametrize("rule", RULES)
+def test_early_termination_equals_fixed_iteration_decodes(cuda_device, rule):
+    """early_stop=True: a codeword stops once all check nodes are satisfied. Its output must equal the
+    plain decoder run with num_iter = the reported iteration count, bit for bit; non-converging codewords run num_iter
+    iterations; at high SNR the average iteration count is a fraction of num_iter while BLER is unchanged."""
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    rng = np.random.default_rng(404)
+    k, n, it = 1024, 2048, 20
+    enc_r = O.LDPC5GEncoderRef(k, n)
+    u = rng.integers(0, 2, (96, k))
+    c = enc_r(u)
+    llr = np.concatenate([_noisy_llr(c[:32], 0.0, k / n, rng), _noisy_llr(c[32:64], 2.2, k / n, rng), _noisy_llr(c[64:], 5.0, k / n, rng)])
+    x = torch.from_numpy(llr).to(cuda_device)
+    enc = LDPC5GEncoder(k, n)
+    dec = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=it, early_stop=True)
+    y = dec(x).cpu().numpy()
+    iters = dec.num_iter_run.cpu().numpy()
+    assert iters.shape == (96,) and iters.min() >= 2 and iters.max() <= it
+    assert np.all(iters[:32] == it)                                # far below the threshold: never converges
+    assert iters[64:].mean() < 6 and iters[32:64].mean() < it      # high SNR: a few iterations
+    for v in np.unique(iters):
+        sel = np.nonzero(iters == v)[0]
+        ref = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=int(v))(x[sel]).cpu().numpy()
+        assert np.array_equal(y[sel], ref), (rule, v)
+    full = LDPC5GDecoder(enc, cn_update=rule, hard_out=True, num_iter=it)(x).cpu().numpy()
+    early = LDPC5GDecoder(enc, cn_update=rule, hard_out=True, num_iter=it, early_stop=True)(x).cpu().numpy()
+    assert np.array_equal((full[32:] != u[32:]).any(1), (early[32:] != u[32:]).any(1))     # same block errors where it matters
+    with pytest.raises(Exception):
+        LDPC5GDecoder(enc, early_stop=True, sum_order="reference")(x)                      # generic kernel: unsupported
