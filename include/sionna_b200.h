@@ -316,6 +316,13 @@ int sb_pusch_ls_combine(float* d_h, float* d_err_var, int64_t rows, int32_t num_
  * -> d_x_hat [num, K] complex, d_no_eff [num, K] real. 1 <= K <= 16, K <= M. */
 int sb_lmmse_equalize(const float* d_y, const float* d_h, const float* d_s, float* d_x_hat, float* d_no_eff, int64_t num,
                       int32_t M, int32_t K, void* stream);
+/* The reference's small dense helpers as callable kernels (complex64, one thread per matrix):
+ *   mode 0  inv_cholesky(s)          utils/linalg.py:8-32         d_s [num, M, M] -> d_out0 = L^-1 [num, M, M]
+ *   mode 1  whiten_channel(y, h, s)  mimo/utils.py:292-357        -> d_out0 = L^-1 y [num, M], d_out1 = L^-1 H [num, M, K]
+ *   mode 2  lmmse_matrix(h, s)       mimo/equalization.py:11-99   -> d_out0 = G [num, K, M]; d_s == NULL: (H^H H + I)^-1 H^H
+ *   mode 3  lmmse_equalizer(y, h, s, whiten_interference=False) :183-233 -> d_out0 = x_hat [num, K], d_out1 = no_eff (fp32) */
+int sb_mimo_linalg(int32_t mode, const float* d_y, const float* d_h, const float* d_s, float* d_out0, void* d_out1,
+                   int64_t num, int32_t M, int32_t K, void* stream);
 /* OFDMEqualizer.call with the LMMSE equaliser fused in (ofdm/equalization.py:109-275 + mimo/equalization.py:101-233):
  * d_y [batch, num_rx, num_rx_ant, num_symbols, num_subcarriers] (effective subcarriers), d_h_hat [batch, num_rx,
  * num_rx_ant, num_tx_streams, num_symbols, num_subcarriers], d_err_var addressed with h_ev_stride[6] (elements; 0 =

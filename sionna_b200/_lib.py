@@ -68,6 +68,7 @@ SIGNATURES = {
     "sb_pusch_precode": (i32, [vp, vp, vp, i64, i32, i32, i32, i64, vp]),
     "sb_pusch_ls_combine": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "sb_lmmse_equalize": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "sb_mimo_linalg": (i32, [i32, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "sb_ofdm_frontend": (i32, [vp] * 15 + [i64] + [i32] * 11 + [vp]),
     "sb_ofdm_lmmse": (i32, [vp] * 12 + [i64] + [i32] * 8 + [vp]),
 }

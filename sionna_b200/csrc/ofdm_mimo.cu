@@ -581,6 +581,129 @@ __global__ void lmmse_kernel(const float2* __restrict__ y, const float2* __restr
     }
 }
 
+// ---- the reference's small dense helpers as callable kernels (thread per matrix, scratch interleaved in shared memory) ---
+//   mode 0  inv_cholesky(s)            utils/linalg.py:8-32          out0 = L^-1 [R, M, M] (lower triangular)
+//   mode 1  whiten_channel(y, h, s)    mimo/utils.py:292-357         out0 = L^-1 y [R, M], out1 = L^-1 H [R, M, K]
+//   mode 2  lmmse_matrix(h, s)         mimo/equalization.py:11-99    out0 = G = H^H (H H^H + S)^-1 [R, K, M]; s == nullptr:
+//                                                                    G = (H^H H + I)^-1 H^H
+//   mode 3  lmmse_equalizer(whiten_interference=False)  :183-233     out0 = x_hat [R, K], out1 = no_eff [R, K] (float)
+__device__ void chol_lower(const Scratch& A, int n) {
+    for (int j = 0; j < n; ++j) {
+        float d = A(j * n + j).x;
+        for (int k = 0; k < j; ++k) { float2 l = A(j * n + k); d -= l.x * l.x + l.y * l.y; }
+        d = sqrtf(d);
+        A(j * n + j) = make_float2(d, 0.f);
+        for (int i = j + 1; i < n; ++i) {
+            float2 v = A(i * n + j);
+            for (int k = 0; k < j; ++k) v = csub(v, cmulc(A(i * n + k), A(j * n + k)));
+            A(i * n + j) = make_float2(v.x / d, v.y / d);
+        }
+    }
+}
+// solve (C C^H) x = b in place for one column held in X(i * ldx + col), C lower triangular n x n
+__device__ void chol_solve_col(const Scratch& C, int n, const Scratch& X, int ldx, int col) {
+    for (int i = 0; i < n; ++i) {
+        float2 v = X(i * ldx + col);
+        for (int k = 0; k < i; ++k) v = csub(v, cmul(C(i * n + k), X(k * ldx + col)));
+        float d = C(i * n + i).x;
+        X(i * ldx + col) = make_float2(v.x / d, v.y / d);
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        float2 v = X(i * ldx + col);
+        for (int k = i + 1; k < n; ++k) { float2 c = C(k * n + i); c.y = -c.y; v = csub(v, cmul(c, X(k * ldx + col))); }
+        float d = C(i * n + i).x;
+        X(i * ldx + col) = make_float2(v.x / d, v.y / d);
+    }
+}
+
+__global__ void mimo_linalg_kernel(int mode, const float2* __restrict__ y, const float2* __restrict__ h,
+                                   const float2* __restrict__ s, float2* __restrict__ out0, void* __restrict__ out1v,
+                                   long long R, int M, int K) {
+    extern __shared__ float2 smem[];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int N = (mode == 2 && s == nullptr) ? K : M;             // order of the matrix that is factorised
+    Scratch A{smem, T, t}, H{smem + (size_t)M * M * T, T, t}, X{smem + (size_t)(M * M + M * K) * T, T, t};
+    for (long long r = (long long)blockIdx.x * T + t; r < R; r += (long long)gridDim.x * T) {
+        if (h) for (int e = 0; e < M * K; ++e) H(e) = h[r * M * K + e];
+        if (mode <= 1) {                                            // L = chol(S), then L^-1 by forward substitution
+            for (int e = 0; e < M * M; ++e) A(e) = s[r * M * M + e];
+            chol_lower(A, M);
+            if (mode == 0) {
+                for (int c = 0; c < M; ++c)
+                    for (int i = 0; i < M; ++i) {
+                        float2 v = make_float2(i == c ? 1.f : 0.f, 0.f);
+                        for (int k = c; k < i; ++k) v = csub(v, cmul(A(i * M + k), X(k * M + c)));
+                        float d = A(i * M + i).x;
+                        X(i * M + c) = i < c ? make_float2(0.f, 0.f) : make_float2(v.x / d, v.y / d);
+                    }
+                for (int e = 0; e < M * M; ++e) out0[r * M * M + e] = X(e);
+            } else {
+                float2* hw = reinterpret_cast<float2*>(out1v);
+                for (int i = 0; i < M; ++i) {
+                    float d = A(i * M + i).x;
+                    float2 v = y[r * M + i];
+                    for (int k = 0; k < i; ++k) v = csub(v, cmul(A(i * M + k), X(k)));
+                    X(i) = make_float2(v.x / d, v.y / d);
+                    for (int c = 0; c < K; ++c) {
+                        float2 w = H(i * K + c);
+                        for (int k = 0; k < i; ++k) w = csub(w, cmul(A(i * M + k), H(k * K + c)));
+                        H(i * K + c) = make_float2(w.x / d, w.y / d);
+                    }
+                }
+                for (int i = 0; i < M; ++i) out0[r * M + i] = X(i);
+                for (int e = 0; e < M * K; ++e) hw[r * M * K + e] = H(e);
+            }
+            continue;
+        }
+        // modes 2, 3: G
+        if (N == M) {                                               // G^H = (H H^H + S)^-1 H, column by column
+            for (int a = 0; a < M; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    float2 acc = s[r * M * M + a * M + b];
+                    for (int k = 0; k < K; ++k) acc = cadd(acc, cmulc(H(a * K + k), H(b * K + k)));
+                    A(a * M + b) = acc;
+                }
+            chol_lower(A, M);
+            for (int e = 0; e < M * K; ++e) X(e) = H(e);
+            for (int c = 0; c < K; ++c) chol_solve_col(A, M, X, K, c);     // X = G^H [M, K]
+        } else {                                                    // G = (H^H H + I)^-1 H^H, X = G [K, M]
+            for (int a = 0; a < K; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    float2 acc = make_float2(a == b ? 1.f : 0.f, 0.f);
+                    for (int m = 0; m < M; ++m) acc = cadd(acc, cmulc(H(m * K + b), H(m * K + a)));
+                    A(a * K + b) = acc;
+                }
+            chol_lower(A, K);
+            for (int m = 0; m < M; ++m) {
+                for (int k = 0; k < K; ++k) { float2 v = H(m * K + k); v.y = -v.y; X(k * M + m) = v; }
+                chol_solve_col(A, K, X, M, m);
+            }
+        }
+        if (mode == 2) {
+            for (int k = 0; k < K; ++k)
+                for (int m = 0; m < M; ++m) {
+                    float2 g = X(k * M + m);
+                    if (N == M) { g = X(m * K + k); g.y = -g.y; }                  // G = (G^H)^H
+                    out0[(r * K + k) * M + m] = g;
+                }
+        } else {
+            float* ne = reinterpret_cast<float*>(out1v);
+            for (int k = 0; k < K; ++k) {
+                float2 gy = make_float2(0.f, 0.f), dd = make_float2(0.f, 0.f);
+                for (int m = 0; m < M; ++m) {
+                    float2 g = X(m * K + k);
+                    g.y = -g.y;
+                    gy = cadd(gy, cmul(g, y[r * M + m]));
+                    dd = cadd(dd, cmul(g, H(m * K + k)));
+                }
+                out0[r * K + k] = cdiv(gy, dd);
+                float2 inv = cdiv(make_float2(1.f, 0.f), dd);
+                ne[r * K + k] = inv.x - 1.f;
+            }
+        }
+    }
+}
+
 // OFDMEqualizer + LMMSE fused. Per (b, rx, sym, sc):
 //   y    [B, RX, ANT, S, F]          (effective subcarriers only)
 //   hhat [B, RX, ANT, TXS, S, F]     TXS = num_tx * num_streams_per_tx
@@ -1255,6 +1378,28 @@ extern "C" int sb_lmmse_equalize(const float* d_y, const float* d_h, const float
     int grid = grid_for(num, threads);
     lmmse_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>((const float2*)d_y, (const float2*)d_h, (const float2*)d_s,
                                                                (float2*)d_x_hat, d_no_eff, num, M, K);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int sb_mimo_linalg(int32_t mode, const float* d_y, const float* d_h, const float* d_s, float* d_out0, void* d_out1,
+                              int64_t num, int32_t M, int32_t K, void* stream) {
+    if (num == 0) return SB_OK;
+    SB_CHECK_ARG(mode >= 0 && mode <= 3 && num > 0 && M >= 1 && d_out0, "sb_mimo_linalg: bad arguments");
+    SB_CHECK_ARG(mode == 0 ? (d_s != nullptr) : (d_h && K >= 1 && K <= M), "sb_mimo_linalg: missing input / need 1 <= K <= M");
+    SB_CHECK_ARG(mode != 1 || (d_y && d_s && d_out1), "sb_mimo_linalg: whiten_channel needs y, h, s and two outputs");
+    SB_CHECK_ARG(mode != 3 || (d_y && d_s && d_out1), "sb_mimo_linalg: the equaliser needs y, h, s and two outputs");
+    if (mode == 0) K = M;
+    const size_t per_thread = sizeof(float2) * ((size_t)M * M + 2 * (size_t)M * K);
+    int dev = 0, optin = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    SB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int threads = (int)std::min<size_t>(128, (size_t)optin / per_thread) / 32 * 32;
+    if (threads < 32) { sb_set_error("sb_mimo_linalg: M = %d too large for the per-thread shared-memory path", M); return SB_EUNSUPPORTED; }
+    const size_t smem = per_thread * threads;
+    SB_CUDA(cudaFuncSetAttribute(mimo_linalg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mimo_linalg_kernel<<<grid_for(num, threads), threads, smem, (cudaStream_t)stream>>>(
+        mode, (const float2*)d_y, (const float2*)d_h, (const float2*)d_s, (float2*)d_out0, d_out1, num, M, K);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

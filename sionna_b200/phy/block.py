@@ -7,9 +7,17 @@ device, runs ``build(*arg_shapes, **kwarg_shapes)`` exactly once (block.py:144-1
 the C-ABI kernels read and write through ``data_ptr()``.
 """
 from abc import ABC, abstractmethod
+import warnings
 import numpy as np
 import torch
 from .config import config, dtypes
+
+
+class PrecisionWarning(UserWarning):
+    """A block configured with precision="double" ran on the single-precision kernels."""
+
+
+_warned_double = set()
 
 
 class Object(ABC):
@@ -101,10 +109,63 @@ class Block(Object):
                 return ()
         return ()
 
+    # precision="double": every kernel of this package computes in fp32 / complex64. A block set to double precision
+    # keeps the reference's I/O contract (float64 / complex128 in and out, block.py:25-31, 122-131) but FALLS BACK to the
+    # single-precision kernels for the arithmetic and says so once per block class (PrecisionWarning); pure data-movement
+    # blocks (resource-grid gathers) stay exact. Results therefore carry fp32 accuracy.
+    def _call_double_fallback(self, args, kwargs):
+        cls = type(self).__name__
+        if cls not in _warned_double:
+            _warned_double.add(cls)
+            warnings.warn(f"{cls}: precision='double' falls back to the single-precision (fp32 / complex64) kernels; "
+                          "inputs and outputs are float64 / complex128, the arithmetic is not.", PrecisionWarning,
+                          stacklevel=3)
+
+        def narrow(v):
+            if isinstance(v, torch.Tensor):
+                if v.dtype == torch.float64:
+                    return v.to(torch.float32)
+                if v.dtype == torch.complex128:
+                    return v.to(torch.complex64)
+            return v
+
+        def widen(v):
+            if isinstance(v, torch.Tensor):
+                if v.dtype == torch.float32:
+                    return v.to(torch.float64)
+                if v.dtype == torch.complex64:
+                    return v.to(torch.complex128)
+            return v
+        args, kwargs = _map_structure(narrow, [list(args), kwargs])
+        self._precision = "single"
+        try:
+            out = self.call(*args, **kwargs)
+        finally:
+            self._precision = "double"
+        return _map_structure(widen, out)
+
     def __call__(self, *args, **kwargs):
         args, kwargs = _map_structure(self._convert_to_tensor, [list(args), kwargs])
         if not self._built:
             shapes = [[self._get_shape(a) for a in args], {k: self._get_shape(v) for k, v in kwargs.items()}]
             self.build(*shapes[0], **shapes[1])
             self._built = True
+        return self._invoke(*args, **kwargs)
+
+    def _invoke(self, *args, **kwargs):
+        """``call`` with the double-precision fallback; blocks that override ``__call__`` go through here as well."""
+        if self._precision == "double" and not getattr(self, "_native_double", False):
+            return self._call_double_fallback(list(args), kwargs)
         return self.call(*args, **kwargs)
+
+
+def fallback_to_single(name, precision):
+    """For free functions with a ``precision`` argument: True if the caller asked for double precision (the result is
+    then computed by the single-precision kernel and widened; warns once per function)."""
+    if (precision or config.precision) != "double":
+        return False
+    if name not in _warned_double:
+        _warned_double.add(name)
+        warnings.warn(f"{name}: precision='double' falls back to the single-precision (fp32 / complex64) kernel.",
+                      PrecisionWarning, stacklevel=3)
+    return True

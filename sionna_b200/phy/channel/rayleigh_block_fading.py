@@ -16,7 +16,7 @@ class RayleighBlockFading(Block):
         self.num_rx, self.num_rx_ant, self.num_tx, self.num_tx_ant = num_rx, num_rx_ant, num_tx, num_tx_ant
 
     def __call__(self, batch_size, num_time_steps, sampling_frequency=None):
-        return self.call(batch_size, num_time_steps, sampling_frequency)
+        return self._invoke(batch_size, num_time_steps, sampling_frequency)
 
     def call(self, batch_size, num_time_steps, sampling_frequency=None):
         h = complex_normal([batch_size, self.num_rx, self.num_rx_ant, self.num_tx, self.num_tx_ant, 1, 1])

@@ -67,8 +67,12 @@ def _cir_convert(a, tau, x, mode, scale, normalize, denom):
     """Common body of cir_to_ofdm_channel / cir_to_time_channel: h[..., t, j] = c_link * sum_p a[..., p, t] e[p, j] with
     e from ``sb_phase_table`` (mode 0: exp(-j 2 pi x_j tau_p); mode 1: sinc(x_j - tau_p * scale)), the per-link
     normalisation from ``sb_cir_gram`` + ``sb_cir_link_scale`` and the contraction by ``sb_cir_apply``."""
+    if a.dtype == torch.complex128:                          # double precision: single-precision kernels, widened result
+        from ..block import fallback_to_single
+        fallback_to_single("cir_to_ofdm_channel / cir_to_time_channel", "double")
+        return _cir_convert(a.to(torch.complex64), tau, x, mode, scale, normalize, denom).to(torch.complex128)
     if a.dtype != torch.complex64:
-        raise NotImplementedError("CIR conversion kernels are complex64 (precision='single').")
+        raise TypeError("a must be a complex tensor")
     if a.dim() != 7:
         raise ValueError("a must have shape [batch, num_rx, num_rx_ant, num_tx, num_tx_ant, num_paths, num_time_steps]")
     dev = a.device
@@ -225,7 +229,7 @@ class TDL(Block):
             print("Warning: The delay spread cannot be set with this model")
 
     def __call__(self, batch_size, num_time_steps=1, sampling_frequency=1.0):
-        return self.call(batch_size, num_time_steps, sampling_frequency)
+        return self._invoke(batch_size, num_time_steps, sampling_frequency)
 
     def draws(self, batch_size):
         """The random draws of one call: (doppler [B], theta [B, P, Ns], phi [B, A, P, Ns], phi0 [B] | None)."""

@@ -60,7 +60,9 @@ class RaggedMessages:
 
     def reduce_sum(self):
         """Sum over the ragged axis -> ``[num_nodes, batch]`` (``tf.reduce_sum(x, axis=1)``)."""
-        return self._reduce("sum")
+        out = torch.zeros((self.nrows(),) + tuple(self.flat_values.shape[1:]), dtype=self.flat_values.dtype,
+                          device=self.flat_values.device)
+        return out.index_add_(0, self.value_rowids(), self.flat_values)
 
     def reduce_prod(self):
         return self._reduce("prod")

@@ -16,7 +16,7 @@ class GaussianPriorSource(Block):
         super().__init__(precision=precision, **kwargs)
 
     def __call__(self, output_shape, no=None, mi=None):
-        return self.call(output_shape, no, mi)
+        return self._invoke(output_shape, no, mi)
 
     def call(self, output_shape, no=None, mi=None):
         if no is None:

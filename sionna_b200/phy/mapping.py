@@ -200,7 +200,7 @@ class Mapper(Block):
             raise ValueError("The last input dimension must be a multiple of num_bits_per_symbol.")
         out_shape = list(bits.shape[:-1]) + [bits.shape[-1] // m]
         n_sym = bits.numel() // m
-        pts = self._constellation()
+        pts = self._constellation().to(torch.complex64)          # the kernels read complex64 points
         x = torch.empty(out_shape, dtype=torch.complex64, device=self.device)
         idx = torch.empty(out_shape, dtype=torch.int32, device=self.device) if self._return_indices else None
         check(lib().sb_qam_map(ptr(bits), ptr(pts), m, ptr(x), ptr(idx), n_sym, current_stream()), "sb_qam_map")
@@ -289,7 +289,7 @@ class Demapper(Block):
             else:
                 pr_t, pr_inner = p.expand(list(y.shape) + [m]).contiguous().reshape(-1), 1
         llr = torch.empty(list(y.shape[:-1]) + [y.shape[-1] * m], dtype=torch.float32, device=dev)
-        pts = self._constellation()
+        pts = self._constellation().to(torch.complex64)          # the kernels read complex64 points
         levels = self._separable_levels(pts) if prior is None else None
         if levels is not None:                                  # square QAM: per-dimension kernel
             check(lib().sb_demap_qam(ptr(y), ptr(no_t), no_inner, ptr(levels[0]), ptr(levels[1]), m, self._method,
@@ -322,7 +322,7 @@ class BinarySource(Block):
         self._offset = 0
 
     def __call__(self, inputs):
-        return self.call(inputs)
+        return self._invoke(inputs)
 
     def call(self, inputs):
         shape = [int(s) for s in (inputs.tolist() if hasattr(inputs, "tolist") else inputs)]
@@ -373,7 +373,7 @@ class SymbolSource(Block):
         self._mapper = Mapper(constellation=constellation, return_indices=return_indices, precision=precision)
 
     def __call__(self, inputs):
-        return self.call(inputs)
+        return self._invoke(inputs)
 
     def call(self, inputs):
         shape = [int(v) for v in (inputs.tolist() if hasattr(inputs, "tolist") else inputs)]

@@ -22,10 +22,9 @@ from .metrics import ErrorCounter
 def complex_normal(shape, var=1.0, precision=None):
     """Complex normal tensor with total variance ``var`` (``var/2`` per real dimension), misc.py:19-54.
     Drawn on the device by ``sb_awgn`` (Philox4x32-10 + Box-Muller) from zeros."""
-    if precision is None:
-        precision = config.precision
-    if precision != "single":
-        raise NotImplementedError("complex_normal: only precision='single' is available.")
+    from ..block import fallback_to_single
+    if fallback_to_single("complex_normal", precision):
+        return complex_normal(shape, var, "single").to(torch.complex128)
     shape = [int(s) for s in shape]
     dev = config.device
     n = int(np.prod(shape)) if len(shape) else 1

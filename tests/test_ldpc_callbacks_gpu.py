@@ -151,3 +151,20 @@ def test_callable_node_updates(cuda_device):
     assert torch.allclose(got_c, ref, rtol=1e-5, atol=1e-4)
     got_both = LDPC5GDecoder(enc, cn_update=cn_minsum, vn_update=vn_sum, hard_out=True, num_iter=6)(x)
     assert torch.equal(got_both, LDPC5GDecoder(enc, cn_update="minsum", hard_out=True, num_iter=6)(x))
+
+
+def test_ragged_messages_reductions(cuda_device):
+    from sionna_b200.phy.fec.ldpc import RaggedMessages
+    rng = np.random.default_rng(1)
+    lens = np.array([3, 1, 5, 2, 4])
+    splits = np.concatenate([[0], np.cumsum(lens)])
+    v = rng.normal(size=(lens.sum(), 6)).astype(np.float32)
+    r = RaggedMessages(torch.from_numpy(v).to(cuda_device), torch.from_numpy(splits).to(cuda_device))
+    seg = [v[splits[i]:splits[i + 1]] for i in range(len(lens))]
+    assert r.shape == (5, None, 6)
+    np.testing.assert_allclose(r.reduce_sum().cpu().numpy(), np.stack([s.sum(0) for s in seg]), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(r.reduce_prod().cpu().numpy(), np.stack([s.prod(0) for s in seg]), rtol=1e-5)
+    np.testing.assert_array_equal(r.reduce_min().cpu().numpy(), np.stack([s.min(0) for s in seg]))
+    np.testing.assert_array_equal(r.reduce_max().cpu().numpy(), np.stack([s.max(0) for s in seg]))
+    np.testing.assert_array_equal(r.gather_rows(r.reduce_max()).cpu().numpy(), np.concatenate([np.repeat(s.max(0)[None], len(s), 0) for s in seg]))
+    assert r.value_rowids().tolist() == np.repeat(np.arange(5), lens).tolist()

@@ -294,3 +294,37 @@ def test_fused_front_end_equals_the_separate_blocks(cuda_device, cfg):
     # not fusable: interfering streams
     sm2 = StreamManagement(np.array([[1, 0], [0, 1]]), 1)
     assert not fusable(_grid(2, 1), sm2, LSChannelEstimator(_grid(2, 1), "nn"), None)
+
+
+def test_whiten_channel_lmmse_matrix_inv_cholesky_and_unwhitened_equaliser(cuda_device):
+    """The reference's helper functions as kernels (sb_mimo_linalg): inv_cholesky (utils/linalg.py:8-32), whiten_channel
+    (mimo/utils.py:292-357), lmmse_matrix with and without S (mimo/equalization.py:11-99) and
+    lmmse_equalizer(whiten_interference=False) (:183-233) against complex128 NumPy."""
+    from sionna_b200.phy.mimo import whiten_channel, lmmse_matrix, lmmse_equalizer
+    from sionna_b200.phy.utils import inv_cholesky
+    rng = np.random.default_rng(12)
+    for m, k in ((8, 3), (16, 4), (4, 4), (2, 1)):
+        num = (7, 11)
+        h = _c64(rng, num + (m, k))
+        a = _c64(rng, num + (m, m))
+        s = (0.3 * np.eye(m) + a @ a.conj().swapaxes(-1, -2) / m).astype(np.complex64)
+        y = _c64(rng, num + (m,))
+        hd, sd, yd = (torch.from_numpy(v).to(cuda_device) for v in (h, s, y))
+        l = np.linalg.cholesky(s.astype(complex))
+        l_inv = np.linalg.inv(l)
+        np.testing.assert_allclose(inv_cholesky(sd).cpu().numpy(), l_inv, rtol=2e-4, atol=2e-5)
+        yw, hw, sw = whiten_channel(yd, hd, sd)
+        np.testing.assert_allclose(yw.cpu().numpy(), (l_inv @ y[..., None].astype(complex))[..., 0], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(hw.cpu().numpy(), l_inv @ h.astype(complex), rtol=2e-4, atol=2e-5)
+        assert torch.equal(sw, torch.eye(m, dtype=torch.complex64, device=cuda_device).expand(*num, m, m))
+        hh = h.astype(complex)
+        g_ref = hh.conj().swapaxes(-1, -2) @ np.linalg.inv(hh @ hh.conj().swapaxes(-1, -2) + s.astype(complex))
+        np.testing.assert_allclose(lmmse_matrix(hd, sd).cpu().numpy(), g_ref, rtol=5e-4, atol=5e-5)
+        g1 = np.linalg.inv(hh.conj().swapaxes(-1, -2) @ hh + np.eye(k)) @ hh.conj().swapaxes(-1, -2)
+        np.testing.assert_allclose(lmmse_matrix(hd).cpu().numpy(), g1, rtol=5e-4, atol=5e-5)
+        x1, n1 = lmmse_equalizer(yd, hd, sd, whiten_interference=False)
+        x0, n0 = lmmse_equalizer(yd, hd, sd)
+        xr, nr = F.lmmse_equalizer(y.astype(complex), hh, s.astype(complex))
+        np.testing.assert_allclose(x1.cpu().numpy(), xr, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(n1.cpu().numpy(), nr, rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(x1.cpu().numpy(), x0.cpu().numpy(), rtol=1e-3, atol=1e-4)

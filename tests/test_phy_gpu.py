@@ -273,3 +273,38 @@ def test_sim_ber_device_modes_keep_reference_stopping_semantics(cuda_device):
         return sim_ber.CALLBACK_NEXT_SNR if mc_iter == 2 else sim_ber.CALLBACK_CONTINUE
     sim_ber(mc_fun, [0.0], batch_size=5, max_mc_iter=10, callback=cb, verbose=False)
     assert seen == [(0, 1, 50), (1, 2, 100), (2, 3, 150)]
+
+
+def test_double_precision_falls_back_to_the_single_precision_kernels(cuda_device):
+    """precision="double" (reference block.py:25-31): blocks accept / return float64 / complex128 and warn once that the
+    arithmetic runs on the fp32 kernels; values equal the single-precision results; pure gathers stay bit exact."""
+    import warnings
+    from sionna_b200.phy.block import PrecisionWarning
+    from sionna_b200.phy.mapping import Mapper, Demapper, BinarySource
+    from sionna_b200.phy.channel import AWGN
+    from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
+    from sionna_b200.phy.mimo import lmmse_equalizer
+    from sionna_b200.phy import config
+    config.seed = 3
+    k, n = 200, 400
+    b = BinarySource()([16, k])
+    enc_d, enc_s = LDPC5GEncoder(k, n, precision="double"), LDPC5GEncoder(k, n)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        c = enc_d(b.double())
+        x = Mapper("qam", 4, precision="double")(c)
+        y = AWGN(precision="double")(x, 0.05)
+        llr = Demapper("app", "qam", 4, precision="double")(y, 0.05)
+        u = LDPC5GDecoder(enc_d, num_iter=10, hard_out=False, precision="double")(llr)
+    assert any(issubclass(i.category, PrecisionWarning) for i in w)
+    assert c.dtype == torch.float64 and x.dtype == torch.complex128 and llr.dtype == torch.float64 and u.dtype == torch.float64
+    assert torch.equal(c.float(), enc_s(b))
+    llr_s = Demapper("app", "qam", 4)(y.to(torch.complex64), 0.05)
+    assert torch.equal(llr.float(), llr_s)
+    assert torch.equal(u.float(), LDPC5GDecoder(enc_s, num_iter=10, hard_out=False)(llr_s))
+    rng = np.random.default_rng(0)
+    h = torch.from_numpy(rng.normal(size=(5, 4, 2)) + 1j * rng.normal(size=(5, 4, 2))).to(cuda_device)
+    yv = torch.from_numpy(rng.normal(size=(5, 4)) + 1j * rng.normal(size=(5, 4))).to(cuda_device)
+    s = torch.eye(4, dtype=torch.complex128, device=cuda_device) * 0.1
+    xh, ne = lmmse_equalizer(yv, h, s, precision="double")
+    assert xh.dtype == torch.complex128 and ne.dtype == torch.float64
