@@ -118,8 +118,8 @@ int sb_ldpc_decode(const sb_ldpc_graph* g, const float* d_llr, int64_t batch, in
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Same decode with opt-in EARLY TERMINATION (the reference always runs num_iter iterations,
- * decoding.py:105-107): a codeword stops as soon as every check node is satisfied by the signs of its incoming messages
- * (the criterion of the reference's DecoderStatisticsCallback, ldpc/utils.py:131-140), at most max_iter iterations.
+ * decoding.py:105-107): a codeword stops as soon as the hard decisions of all its variable nodes satisfy every parity check
+ * (H x_hat = 0, evaluated on chip before each iteration), at most max_iter iterations.
  * d_num_iter [batch] (optional) receives the iterations run per codeword; the outputs of a codeword equal those of
  * sb_ldpc_decode with num_iter = d_num_iter[b] bit for bit. Only for graphs on the quasi-cyclic on-chip path (flooding,
  * "sum" VN rule); SB_EUNSUPPORTED otherwise. */

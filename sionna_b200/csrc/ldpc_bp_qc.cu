@@ -45,8 +45,9 @@ struct QcParams {
     float* state_out;
     long long B;
     int num_iter, hard_out, use_tma;
-    int early;               // opt-in early termination: stop once every check node is satisfied (see the kernel)
+    int early;               // opt-in early termination by the syndrome of the hard decisions (see the kernel)
     int* iters_out;          // [B] iterations actually run per codeword, or nullptr
+    const int2* row_edge;    // [nnz] per base entry (processing order): {column * Z, shift}  (syndrome pass only)
     int tab_rep;             // copies of the phi log table in shared memory (32, 8 or 1; 0: rule does not use it)
     float offset, llr_max;
 };
@@ -77,7 +78,7 @@ struct QcParams {
 // which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
 template <bool SC, class LT>
 __device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
-                                          const LT& lt, int* unsat) {
+                                          const LT& lt) {
     const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
@@ -112,7 +113,6 @@ SB_UNROLL(SB_PHI_UNROLL)
         *q0 = __uint_as_float(__float_as_uint(p) | (b0 & 0x80000000u));
     }
     par &= 0x80000000u;
-    if (unsat && par) *unsat = 1;                         // early termination: this check is not satisfied
     float yP = 0.f;                                       // phi(P), evaluated lazily (2)
     bool have_yP = false;
     l = 0;
@@ -150,14 +150,9 @@ SB_UNROLL(SB_PHI_UNROLL)
     }
 }
 
-__device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip, int* unsat) {
+__device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip) {
     const float atanh_clip = (float)(1 - 1e-7);
     float prod = 1.f;
-    if (unsat) {                                          // sign product of the incoming messages (sign(0) := +1)
-        unsigned par = 0;
-        for (int l = 0; l < deg; ++l) par ^= __float_as_uint(pm[l * Z]);
-        if (par & 0x80000000u) *unsat = 1;
-    }
 #pragma unroll 2
     for (int l = 0; l < deg; ++l) {
         float* q = pm + l * Z;
@@ -181,7 +176,7 @@ __device__ __forceinline__ void cn_tanh_qc(float* pm, int Z, int deg, float clip
 //   unique minimum -> that edge gets fl(fl(m2 - m1) + m1), all others m1;  repeated minimum -> all edges m1.
 // Offset, max(.,0) and clipping act on only two distinct magnitudes and are hoisted out of the edge loop.
 template <int DMAX, bool EXACT>                           // EXACT: deg == DMAX, no per-edge guards
-__device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset, int* unsat) {
+__device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float clip, float offset) {
     float x[DMAX];                                        // every element is assigned unconditionally (registers)
     float m1 = INFINITY, m2 = INFINITY;
     unsigned par = 0;
@@ -196,7 +191,6 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
         par ^= __float_as_uint(v);
     }
     par &= 0x80000000u;
-    if (unsat && par) *unsat = 1;
     float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
     if (deg == 1) min_e = __fadd_rn(100000.f, m1);
     const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
@@ -211,7 +205,7 @@ __device__ __forceinline__ void cn_minsum_qc(float* pm, int Z, int deg, float cl
 }
 
 // generic-degree fallback (re-reads shared memory instead of holding the row in registers)
-__device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, float clip, float offset, int* unsat) {
+__device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, float clip, float offset) {
     float m1 = INFINITY, m2 = INFINITY;
     unsigned par = 0;
     for (int l = 0; l < deg; ++l) {
@@ -222,7 +216,6 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
         par ^= __float_as_uint(v);
     }
     par &= 0x80000000u;
-    if (unsat && par) *unsat = 1;
     float min_e = (m2 == m1) ? m1 : __fadd_rn(__fsub_rn(m2, m1), m1);
     if (deg == 1) min_e = __fadd_rn(100000.f, m1);
     const float o1 = fminf(fmaxf(__fsub_rn(m1, offset), 0.f), clip);
@@ -236,32 +229,32 @@ __device__ __forceinline__ void cn_minsum_qc_loop(float* pm, int Z, int deg, flo
 
 template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_qc(float* pm, int Z, int deg, float clip, float offset, float phi_max, bool sc,
-                                      int* sat_flag, const LT& lt, int* unsat) {
+                                      int* sat_flag, const LT& lt) {
     if (RULE == SB_CN_BOXPLUS_PHI) {
-        if (sc) cn_phi_qc<true, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt, unsat);
-        else cn_phi_qc<false, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt, unsat);
+        if (sc) cn_phi_qc<true, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
+        else cn_phi_qc<false, LT>(pm, Z, deg, clip, phi_max, sat_flag, lt);
     }
-    else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip, unsat);
+    else if (RULE == SB_CN_BOXPLUS) cn_tanh_qc(pm, Z, deg, clip);
     else {
         const float off = (RULE == SB_CN_MINSUM) ? 0.f : offset;
         // exact-degree code for the degrees of the 5G base graphs, guarded buckets otherwise (deg is warp-uniform)
         if (CLS == 4) {
-            if (deg == 3) cn_minsum_qc<3, true>(pm, Z, deg, clip, off, unsat);
-            else if (deg == 4) cn_minsum_qc<4, true>(pm, Z, deg, clip, off, unsat);
-            else cn_minsum_qc<4, false>(pm, Z, deg, clip, off, unsat);
+            if (deg == 3) cn_minsum_qc<3, true>(pm, Z, deg, clip, off);
+            else if (deg == 4) cn_minsum_qc<4, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<4, false>(pm, Z, deg, clip, off);
         } else if (CLS == 3) {
-            if (deg == 5) cn_minsum_qc<5, true>(pm, Z, deg, clip, off, unsat);
-            else if (deg == 6) cn_minsum_qc<6, true>(pm, Z, deg, clip, off, unsat);
-            else if (deg == 7) cn_minsum_qc<7, true>(pm, Z, deg, clip, off, unsat);
-            else cn_minsum_qc<8, true>(pm, Z, deg, clip, off, unsat);
+            if (deg == 5) cn_minsum_qc<5, true>(pm, Z, deg, clip, off);
+            else if (deg == 6) cn_minsum_qc<6, true>(pm, Z, deg, clip, off);
+            else if (deg == 7) cn_minsum_qc<7, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<8, true>(pm, Z, deg, clip, off);
         } else if (CLS == 2) {
-            if (deg == 9) cn_minsum_qc<9, true>(pm, Z, deg, clip, off, unsat);
-            else if (deg == 10) cn_minsum_qc<10, true>(pm, Z, deg, clip, off, unsat);
-            else cn_minsum_qc<12, false>(pm, Z, deg, clip, off, unsat);
+            if (deg == 9) cn_minsum_qc<9, true>(pm, Z, deg, clip, off);
+            else if (deg == 10) cn_minsum_qc<10, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<12, false>(pm, Z, deg, clip, off);
         } else if (CLS == 1) {
-            if (deg == 19) cn_minsum_qc<19, true>(pm, Z, deg, clip, off, unsat);
-            else cn_minsum_qc<20, false>(pm, Z, deg, clip, off, unsat);
-        } else cn_minsum_qc_loop(pm, Z, deg, clip, off, unsat);
+            if (deg == 19) cn_minsum_qc<19, true>(pm, Z, deg, clip, off);
+            else cn_minsum_qc<20, false>(pm, Z, deg, clip, off);
+        } else cn_minsum_qc_loop(pm, Z, deg, clip, off);
     }
 }
 
@@ -394,12 +387,12 @@ __device__ __forceinline__ int first_of(int start, int start_mod, const WarpCtx&
 template <int RULE, int CLS, class LT>
 __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, float* msg, const float* llr_s,
                                          const int4* s_row, int start, int end, float clip, bool fuse,
-                                         float phi_max, bool sc, int* sat_flag, const LT& lt, int* unsat) {
+                                         float phi_max, bool sc, int* sat_flag, const LT& lt, unsigned char* hd) {
     for (int rr = first_of(start, p.row_cls_mod[CLS], w); rr < end; rr += w.G) {
         int4 ri = s_row[rr];
         if (w.lane_i < ri.z) {
             float* pm = msg + ri.x * p.Z + w.lane_i;
-            cn_qc<RULE, CLS, LT>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt, unsat);
+            cn_qc<RULE, CLS, LT>(pm, p.Z, ri.y, clip, p.offset, phi_max, sc, sat_flag, lt);
             if (fuse && ri.w >= 0) {
                 // the row's last edge goes to a degree-1 VN: apply that VN's update right here (decoding.py:714-729
                 // with a single incoming message) so the VN phase can skip the column
@@ -410,7 +403,28 @@ __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, fl
                 float c2v = *q;
                 float x_tot = __fadd_rn(__fadd_rn(0.f, c2v), llr_s[vb * p.Z + j]);
                 *q = clipf(__fadd_rn(-c2v, x_tot), clip);
+                if (hd) hd[vb * p.Z + j] = 0.f >= x_tot ? 1 : 0;
             }
+        }
+    }
+}
+
+// Syndrome of the current hard decisions hd[] (one byte per VN): every warp walks its block rows like the CN phase and
+// XORs the decisions of the row's variable nodes, VN of base entry (c, s) and check offset i being c * Z + (i + s) mod Z.
+// Raises *unsat if any check is violated.
+__device__ __forceinline__ void syndrome_pass(const QcParams& p, const WarpCtx& w, const int4* s_row,
+                                              const unsigned char* hd, int* unsat) {
+    for (int rr = w.grp; rr < p.n_rows; rr += w.G) {
+        const int4 ri = s_row[rr];
+        if (w.lane_i < ri.z) {
+            unsigned par = 0;
+            for (int l = 0; l < ri.y; ++l) {
+                const int2 e = __ldg(p.row_edge + ri.x + l);
+                int j = w.lane_i + e.y;
+                j -= (j >= p.Z) ? p.Z : 0;
+                par ^= hd[e.x + j];
+            }
+            if (par) *unsat = 1;
         }
     }
 }
@@ -418,12 +432,13 @@ __device__ __forceinline__ void cn_class(const QcParams& p, const WarpCtx& w, fl
 template <int MODE, int CLS, bool EX>
 __device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
                                          const int4* s_col, uint32_t s_ce, int start, int end, float clip,
-                                         bool final_pass, long long b) {
+                                         bool final_pass, long long b, unsigned char* hd) {
     for (int cc = first_of(start, p.col_cls_mod[CLS], w); cc < end; cc += w.G) {
         int4 ci = s_col[cc];
         if (w.lane_i < ci.z) {
             int v = ci.w + w.lane_i;
             float x_tot = vn_cls<MODE, CLS, EX>(msgb, s_ce + 8 * ci.x, ci.y, 4 * w.lane_i, 4 * p.Z, llr_s[v], clip);
+            if (MODE == 0 && hd) hd[v] = 0.f >= x_tot ? 1 : 0;                                // hard decision (:622-624)
             if (MODE == 0 && final_pass) {
                 int o = p.out_pos[v];
                 if (o >= 0) {
@@ -439,19 +454,19 @@ __device__ __forceinline__ void vn_class(const QcParams& p, const WarpCtx& w, ui
 template <int MODE, bool EX>
 __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint32_t msgb, const float* llr_s,
                                        const int4* s_col, uint32_t s_ce, float clip, bool final_pass,
-                                       bool with_fused, long long b) {
+                                       bool with_fused, long long b, unsigned char* hd = nullptr) {
     const int* ce = p.col_cls_end;
-    vn_class<MODE, 0, EX>(p, w, msgb, llr_s, s_col, s_ce, 0, ce[0], clip, final_pass, b);
-    vn_class<MODE, 1, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[0], ce[1], clip, final_pass, b);
-    vn_class<MODE, 2, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[1], ce[2], clip, final_pass, b);
-    vn_class<MODE, 3, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[2], ce[3], clip, final_pass, b);
-    vn_class<MODE, 4, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[3], ce[4], clip, final_pass, b);
-    vn_class<MODE, 5, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[4], ce[5], clip, final_pass, b);
-    vn_class<MODE, 6, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[5], ce[6], clip, final_pass, b);
-    vn_class<MODE, 7, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[6], ce[7], clip, final_pass, b);
-    vn_class<MODE, 8, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[7], ce[8], clip, final_pass, b);
-    vn_class<MODE, 9, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[8], ce[9], clip, final_pass, b);
-    if (with_fused) vn_class<MODE, 10, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b);
+    vn_class<MODE, 0, EX>(p, w, msgb, llr_s, s_col, s_ce, 0, ce[0], clip, final_pass, b, hd);
+    vn_class<MODE, 1, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[0], ce[1], clip, final_pass, b, hd);
+    vn_class<MODE, 2, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[1], ce[2], clip, final_pass, b, hd);
+    vn_class<MODE, 3, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[2], ce[3], clip, final_pass, b, hd);
+    vn_class<MODE, 4, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[3], ce[4], clip, final_pass, b, hd);
+    vn_class<MODE, 5, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[4], ce[5], clip, final_pass, b, hd);
+    vn_class<MODE, 6, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[5], ce[6], clip, final_pass, b, hd);
+    vn_class<MODE, 7, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[6], ce[7], clip, final_pass, b, hd);
+    vn_class<MODE, 8, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[7], ce[8], clip, final_pass, b, hd);
+    vn_class<MODE, 9, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[8], ce[9], clip, final_pass, b, hd);
+    if (with_fused) vn_class<MODE, 10, EX>(p, w, msgb, llr_s, s_col, s_ce, ce[9], ce[10], clip, final_pass, b, hd);
 }
 
 // Threads per CTA. 24 warps (80 registers/thread) for every rule: 30 warps at 64 registers were measured for the min-sum
@@ -476,8 +491,10 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
     int2* s_ce_p = reinterpret_cast<int2*>(smem_raw + off_ce);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_bar);
     int* sat_flag = reinterpret_cast<int*>(smem_raw + off_bar + 8);
-    int* unsat2 = reinterpret_cast<int*>(smem_raw + off_bar + 16);   // [2] "some check is unsatisfied", alternating per iteration
-    const int off_tab = off_bar + 32;                     // phi log table, tab_rep copies interleaved per entry
+    int* unsat = reinterpret_cast<int*>(smem_raw + off_bar + 12);
+    const int off_tab = off_bar + 16;                     // phi log table, tab_rep copies interleaved per entry
+    // early termination: one hard-decision byte per VN behind the table
+    unsigned char* hd = p.early ? smem_raw + off_tab + (RULE == SB_CN_BOXPLUS_PHI ? REP * SB_LOGTAB_N * 8 : 0) : nullptr;
     const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
     const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
             }
         }
         __syncthreads();
-        if (tid == 0) { *sat_flag = 0; unsat2[0] = 0; unsat2[1] = 0; }
+        if (tid == 0) *sat_flag = 0;
         // ---- v2c = llr of the edge's VN (decoding.py:571) ---------------------------------------------------------
         vn_all<1, true>(p, w, msgb, llr_s, s_col, s_ce, clip, false, true, b);
         __syncthreads();
@@ -548,33 +565,34 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
                 }
             }
         }
-        // Early termination (opt-in, the reference has none: decoding.py:105-107): a codeword stops once every check node
-        // is satisfied by the signs of its incoming messages (the convergence criterion of the reference's
-        // DecoderStatisticsCallback, ldpc/utils.py:131-140). The CN phase of iteration `it` reports unsatisfied checks in
-        // unsat2[it & 1]; when none was reported the NEXT iteration becomes the final one (its CN phase must not fuse
-        // the degree-1 updates), so the outputs equal a fixed-iteration decode with num_iter = `limit` bit for bit.
+        // Early termination (opt-in; the reference always runs num_iter iterations, decoding.py:105-107). The VN phase
+        // keeps the hard decision of every VN in hd[]; before iteration `it` (it >= 1) a syndrome pass checks H * hd = 0.
+        // If it holds, iteration `it` becomes the final one (its CN phase does not fuse the degree-1 updates, its VN phase
+        // writes the outputs): the outputs equal a fixed-iteration decode with num_iter = it + 1 bit for bit.
         int limit = p.num_iter;
         for (int it = 0; it < limit; ++it) {
+            if (p.early && it > 0 && it < limit - 1) {
+                if (tid == 0) *unsat = 0;
+                __syncthreads();
+                syndrome_pass(p, w, s_row, hd, unsat);
+                __syncthreads();
+                if (*unsat == 0) limit = it + 1;               // CTA-uniform: read between barriers
+            }
             const bool final_pass = it == limit - 1;
-            int* unsat = p.early ? unsat2 + (it & 1) : nullptr;
             const bool sc = *sat_flag != 0;                // CTA-uniform: read after the barrier that ended the last phase
             // ---- CN phase (degree-1 VN updates fused in, except in the final iteration) -------------------------
             if (final_pass && tid == 0 && p.use_tma && b + gridDim.x < p.B)   // pull the next codeword's logits into L2 early
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.llr + (size_t)(b + gridDim.x) * p.n_in),
                              "r"((uint32_t)p.n_in * 4u) : "memory");
             const int* re = p.row_cls_end;
-            cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
-            cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
-            cn_class<RULE, 2, LogTab<REP>>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
-            cn_class<RULE, 3, LogTab<REP>>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
-            cn_class<RULE, 4, LogTab<REP>>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt, unsat);
+            cn_class<RULE, 0, LogTab<REP>>(p, w, msg, llr_s, s_row, 0, re[0], clip, !final_pass, phi_max, sc, sat_flag, lt, hd);
+            cn_class<RULE, 1, LogTab<REP>>(p, w, msg, llr_s, s_row, re[0], re[1], clip, !final_pass, phi_max, sc, sat_flag, lt, hd);
+            cn_class<RULE, 2, LogTab<REP>>(p, w, msg, llr_s, s_row, re[1], re[2], clip, !final_pass, phi_max, sc, sat_flag, lt, hd);
+            cn_class<RULE, 3, LogTab<REP>>(p, w, msg, llr_s, s_row, re[2], re[3], clip, !final_pass, phi_max, sc, sat_flag, lt, hd);
+            cn_class<RULE, 4, LogTab<REP>>(p, w, msg, llr_s, s_row, re[3], re[4], clip, !final_pass, phi_max, sc, sat_flag, lt, hd);
             __syncthreads();
-            if (p.early) {
-                if (!final_pass && unsat2[it & 1] == 0) limit = it + 2;        // CTA-uniform (read between two barriers)
-                if (tid == 0) unsat2[(it + 1) & 1] = 0;                       // the other slot is idle until the next CN phase
-            }
             // ---- VN phase ---------------------------------------------------------------------------------------
-            vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b);
+            vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b, hd);
             __syncthreads();
         }
         if (p.iters_out && tid == 0) p.iters_out[b] = limit;
@@ -586,9 +604,9 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
     }
 }
 
-size_t qc_smem_bytes(const sb_ldpc_graph* g, int tab_rep) {
-    return ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 16 +
-           (size_t)g->qc_nnz * 8 + 16 + 32 + (size_t)tab_rep * SB_LOGTAB_N * 8;
+size_t qc_smem_bytes(const sb_ldpc_graph* g, int tab_rep, int early = 0) {
+    return (early ? (size_t)g->N + 16 : 0) + ((size_t)g->qc_nnz * g->qc_Z + g->N) * 4 + 16 + (size_t)g->qc_cols * 16 + (size_t)g->qc_rows * 16 +
+           (size_t)g->qc_nnz * 8 + 16 + 16 + (size_t)tab_rep * SB_LOGTAB_N * 8;
 }
 
 template <typename T>
@@ -607,6 +625,7 @@ int qc_ensure_uploaded(sb_ldpc_graph* g) {
     if ((rc = upload_ints(&g->d_qc_in_idx, g->qc_in_idx))) return rc;
     if ((rc = upload_ints(&g->d_qc_out_pos, g->qc_out_pos))) return rc;
     if ((rc = upload_ints(&g->d_qc_slot_of_edge, g->qc_slot_of_edge))) return rc;
+    if ((rc = upload_ints(&g->d_qc_row_edge, g->qc_row_edge))) return rc;
     g->qc_uploaded = true;
     return SB_OK;
 }
@@ -633,7 +652,7 @@ int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t sme
 void sb_qc_free_device(sb_ldpc_graph* g) {
     if (!g->qc_uploaded) return;
     cudaFree(g->d_qc_row_info); cudaFree(g->d_qc_col_info); cudaFree(g->d_qc_col_edge); cudaFree(g->d_qc_in_idx);
-    cudaFree(g->d_qc_out_pos); cudaFree(g->d_qc_slot_of_edge);
+    cudaFree(g->d_qc_out_pos); cudaFree(g->d_qc_slot_of_edge); cudaFree(g->d_qc_row_edge);
     g->qc_uploaded = false;
 }
 
@@ -747,7 +766,7 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
     for (int c = 0; c < n_cols; ++c) for (int k = col_class(c); k < 11; ++k) ++col_cls_end[k];
     // base-entry numbering: rows in processing order, ascending column inside a row
     std::vector<int> be_of((size_t)n_rows * n_cols, -1);
-    std::vector<int> row_info(4 * n_rows);
+    std::vector<int> row_info(4 * n_rows), row_edge;
     int be = 0;
     for (int rr = 0; rr < n_rows; ++rr) {
         int r = rorder[rr];
@@ -758,6 +777,8 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
         for (const Ent& en : by_row[r]) {
             if (be_of[(size_t)en.r * n_cols + en.c] != -1) { sb_set_error("sb_ldpc_graph_set_qc: duplicate base entry"); return SB_EINVAL; }
             be_of[(size_t)en.r * n_cols + en.c] = be++;
+            row_edge.push_back(en.c * Z);
+            row_edge.push_back(en.s);
         }
     }
     const int nnz = be;
@@ -788,7 +809,7 @@ extern "C" int sb_ldpc_graph_set_qc(sb_ldpc_graph* g, int32_t Z, int32_t n_entri
     g->qc_max_col_deg = *std::max_element(cdeg.begin(), cdeg.end());
     g->qc_row_info.swap(row_info); g->qc_col_info.swap(col_info); g->qc_col_edge.swap(col_edge);
     g->qc_row_cls_end = row_cls_end; g->qc_col_cls_end = col_cls_end;
-    g->qc_in_idx.swap(in_nat); g->qc_out_pos.swap(out_nat); g->qc_slot_of_edge.swap(slot);
+    g->qc_in_idx.swap(in_nat); g->qc_out_pos.swap(out_nat); g->qc_slot_of_edge.swap(slot); g->qc_row_edge.swap(row_edge);
     return SB_OK;
 }
 
@@ -830,9 +851,9 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     if (!g->qc || !g->flooding || vn_rule != SB_VN_SUM || d_state_in || cn_rule > SB_CN_OFFSET_MINSUM) return SB_OK;
     // boxplus-phi keeps the log table of phi in shared memory: one copy per bank pair if it fits, else a single copy
     int tab_rep = cn_rule == SB_CN_BOXPLUS_PHI ? 32 : 0;
-    if (tab_rep && qc_smem_bytes(g, tab_rep) > (size_t)g->smem_optin) tab_rep = 8;
-    if (tab_rep && qc_smem_bytes(g, tab_rep) > (size_t)g->smem_optin) tab_rep = 1;
-    const size_t smem = qc_smem_bytes(g, tab_rep);
+    if (tab_rep && qc_smem_bytes(g, tab_rep, early) > (size_t)g->smem_optin) tab_rep = 8;
+    if (tab_rep && qc_smem_bytes(g, tab_rep, early) > (size_t)g->smem_optin) tab_rep = 1;
+    const size_t smem = qc_smem_bytes(g, tab_rep, early);
     if (smem > (size_t)g->smem_optin) return SB_OK;
     if ((cn_rule == SB_CN_MINSUM || cn_rule == SB_CN_OFFSET_MINSUM) &&
         !(llr_max < 100000.f && (float)(g->qc_max_row_deg - 1) * llr_max < 99000.f))
@@ -849,7 +870,7 @@ int sb_qc_try_decode(sb_ldpc_graph* g, const float* d_llr, int64_t batch, int32_
     p.slot_of_edge = g->d_qc_slot_of_edge;
     p.llr = d_llr; p.out = d_out; p.state_out = d_state_out; p.B = batch; p.num_iter = num_iter; p.hard_out = hard_out;
     p.offset = offset; p.llr_max = llr_max; p.tab_rep = tab_rep;
-    p.early = early; p.iters_out = d_iters;
+    p.early = early; p.iters_out = d_iters; p.row_edge = (const int2*)g->d_qc_row_edge;
     p.use_tma = (g->n_in % 4 == 0) && (g->n_in <= p.E_alloc) && ((reinterpret_cast<uintptr_t>(d_llr) & 15) == 0);
     const int Zb = (g->qc_Z + 31) / 32;                    // 32-lane slices per block row (<= 12 for Z <= 384)
     const int max_warps = qc_max_threads(cn_rule) / 32;

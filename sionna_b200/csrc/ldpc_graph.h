@@ -27,9 +27,10 @@ struct sb_ldpc_graph {
     std::vector<int> qc_col_info;   // int4 per base col (processing order): {first col-edge, deg, zcol, c*Z}
     std::vector<int> qc_col_edge;   // int2 per (col, entry), ascending base row: {be*Z*4, s*4 | (zrow*4) << 16}
     std::vector<int> qc_in_idx, qc_out_pos, qc_slot_of_edge;   // natural VN order / reference edge order
+    std::vector<int> qc_row_edge;   // int2 per base entry (processing order): {column * Z, shift} for the syndrome pass
     std::vector<int> qc_row_cls_end, qc_col_cls_end;   // class boundaries in processing order (ldpc_bp_qc.cu)
     int *d_qc_row_info = nullptr, *d_qc_col_info = nullptr, *d_qc_col_edge = nullptr, *d_qc_in_idx = nullptr,
-        *d_qc_out_pos = nullptr, *d_qc_slot_of_edge = nullptr;
+        *d_qc_out_pos = nullptr, *d_qc_slot_of_edge = nullptr, *d_qc_row_edge = nullptr;
     bool qc_uploaded = false;
 };
 

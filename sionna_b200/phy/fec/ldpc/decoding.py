@@ -115,7 +115,7 @@ class LDPCBPDecoder(Block):
     tensors in the reference's layouts and list orders - instead of the fused shared-memory kernels.
 
     Extension (keyword ``early_stop=True``, not in the reference, 5G / quasi-cyclic codes only): every codeword stops
-    as soon as all its check nodes are satisfied instead of always running ``num_iter`` iterations
+    as soon as its hard decisions satisfy all parity checks instead of always running ``num_iter`` iterations
     (decoding.py:105-107); ``decoder.num_iter_run`` then holds the iterations each codeword of the last call ran, and
     its output equals a fixed ``num_iter_run``-iteration decode bit for bit. Off by default.
 
@@ -402,8 +402,8 @@ class LDPCBPDecoder(Block):
         return out, st_out
 
     def _decode_early(self, llr2d, num_iter, msg_v2c):
-        """``early_stop=True``: at most ``num_iter`` iterations, every codeword stops once all its check nodes are
-        satisfied (``sb_ldpc_decode_early``); ``self.num_iter_run`` holds the iterations each codeword ran."""
+        """``early_stop=True``: at most ``num_iter`` iterations, every codeword stops once its hard decisions form a
+        codeword (``sb_ldpc_decode_early``); ``self.num_iter_run`` holds the iterations each codeword ran."""
         if msg_v2c is not None or self._return_state:
             raise ValueError("early_stop cannot be combined with a decoder state (msg_v2c / return_state)")
         if self._vn_rule != _VN_RULES["sum"] or self._cn_rule == _CN_RULES["identity"]:

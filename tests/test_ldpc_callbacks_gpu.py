@@ -85,25 +85,33 @@ def test_generic_pcm_layered_schedule_and_identity_rules(cuda_device):
 def test_statistics_exit_and_weighted_bp_callbacks(cuda_device):
     """The reference's three callbacks (ldpc/utils.py): decoder statistics (all checks satisfied per iteration), EXIT
     mutual information (all-zero codeword), weighted BP (unit weights = plain BP; weights < 1 damp the messages)."""
-    from sionna_b200.phy.fec.ldpc import (LDPC5GEncoder, LDPC5GDecoder, DecoderStatisticsCallback, EXITCallback,
-                                          WeightedBPCallback)
-    from sionna_b200.phy.fec.utils import GaussianPriorSource
+    from sionna_b200.phy.fec.ldpc import (LDPC5GEncoder, LDPC5GDecoder, LDPCBPDecoder, DecoderStatisticsCallback,
+                                          EXITCallback, WeightedBPCallback)
+    from sionna_b200.phy.fec.utils import GaussianPriorSource, load_parity_check_examples
     from sionna_b200.phy import config
     config.seed = 8
-    k, n, bs, it = 500, 1000, 300, 12
-    enc = LDPC5GEncoder(k, n)
-    llr = GaussianPriorSource()([bs, n], no=0.55)                     # all-zero codeword, logits ~ N(-2/no, 4/no)
+    # The statistics callback counts codewords whose check nodes all see an even number of negative messages. In a 5G
+    # graph a degree-1 parity VN keeps sending its channel LLR, so one wrong-sign channel observation keeps its check
+    # "unsatisfied" for ever although the information bits decode: the callback is meaningful on graphs without
+    # degree-1 VNs, e.g. the 802.11n code of the reference's example set (same remark applies to the reference).
+    pcm = load_parity_check_examples(4)[0].astype(np.float64)
+    n, bs, it = pcm.shape[1], 300, 12
+    llr = GaussianPriorSource()([bs, n], no=0.5)                      # all-zero codeword, logits ~ N(-2/no, 4/no)
     stats, exit_c, exit_v = DecoderStatisticsCallback(it), EXITCallback(it), EXITCallback(it)
-    dec = LDPC5GDecoder(enc, num_iter=it, hard_out=True, c2v_callbacks=[stats, exit_c], v2c_callbacks=[exit_v])
+    dec = LDPCBPDecoder(pcm, num_iter=it, hard_out=True, c2v_callbacks=[stats, exit_c], v2c_callbacks=[exit_v])
     u_hat = dec(llr)
     assert stats.num_samples.tolist() == [bs] * it
     succ = stats.num_decoded_cws.numpy()
-    assert np.all(np.diff(succ) >= -2) and succ[-1] >= 0.95 * bs and succ[0] < succ[-1]
+    assert succ[-1] >= 0.8 * bs and succ[0] < succ[-1] and np.all(np.diff(succ) >= -3)
     assert 0.0 < float(stats.avg_number_iterations) < it
-    # a codeword counted as decoded has all checks satisfied: its information bits are error free at this SNR
+    # a codeword whose checks are all satisfied at the end decodes to the all-zero word (or another codeword: rare)
     assert float((u_hat != 0).any(dim=-1).float().mean()) <= 1 - succ[-1] / bs + 0.02
     mi_c, mi_v = exit_c.mi.numpy()[:it], exit_v.mi.numpy()[1:it + 1]
     assert mi_c[-1] > 0.9 and mi_v[-1] > 0.95 and mi_c[-1] > mi_c[0] and mi_v[-1] > mi_v[0]
+    k, n = 500, 1000
+    enc = LDPC5GEncoder(k, n)
+    llr = GaussianPriorSource()([64, n], no=0.55)
+    dec = LDPC5GDecoder(enc, num_iter=5, hard_out=False)
     # weighted BP: unit weights reproduce plain BP bit for bit; damping changes the soft outputs
     plain = LDPC5GDecoder(enc, num_iter=5, hard_out=False, sum_order="reference")(llr)
     wcb = WeightedBPCallback(dec.num_edges)

@@ -318,7 +318,7 @@ def test_full_batch_4096_bit_exact_vs_oracle(cuda_device, rule):
 
 @pytest.mark.parametrize("rule", RULES)
 def test_early_termination_equals_fixed_iteration_decodes(cuda_device, rule):
-    """early_stop=True: a codeword stops once all check nodes are satisfied. Its output must equal the
+    """early_stop=True: a codeword stops once its hard decisions satisfy every check. Its output must equal the
     plain decoder run with num_iter = the reported iteration count, bit for bit; non-converging codewords run num_iter
     iterations; at high SNR the average iteration count is a fraction of num_iter while BLER is unchanged."""
     from sionna_b200.phy.fec.ldpc import LDPC5GEncoder, LDPC5GDecoder
