@@ -581,6 +581,15 @@ def run_ldpc(args):
                 ms = time_calls(lambda it=[0]: (dec_ms(d_in[it[0] & 1]), it.__setitem__(0, it[0] + 1)), 10, warm=3)
                 variants["minsum"] = {"kernel_ms": ms, "value": BATCH * N_CODE / (ms * 1e-3),
                                       "frac": alg / (ms * 1e-3) / 1e9 / peak}
+            try:                                              # opt-in early termination (NOT the reference's semantics)
+                dec_et = LDPC5GDecoder(enc, cn_update=args.cn_update, num_iter=NUM_ITER, hard_out=True, return_infobits=True,
+                                       early_stop=True)
+                ms = time_calls(lambda it=[0]: (dec_et(d_in[it[0] & 1]), it.__setitem__(0, it[0] + 1)), 10, warm=3)
+                variants[f"{args.cn_update} early_stop (opt-in; the reference always runs 20 iterations)"] = {
+                    "kernel_ms": ms, "value": BATCH * N_CODE / (ms * 1e-3),
+                    "mean_iterations": float(dec_et.num_iter_run.float().mean())}
+            except Exception as e:
+                variants["early_stop"] = {"error": repr(e)[:160]}
             line["roofline"]["variants"] = variants
         if not args.no_cpu_baseline and world == 1:           # reported baseline: rank 0 at N = 1 only
             from oracle import ldpc as O

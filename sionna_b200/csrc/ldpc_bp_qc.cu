@@ -471,7 +471,10 @@ __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint
 
 // Threads per CTA. 24 warps (80 registers/thread) for every rule: 30 warps at 64 registers were measured for the min-sum
 // kernels and lost 7 % (5.32 vs 4.97 ms / 4096 codewords: more barrier and spill time than latency hiding gained).
-__host__ __device__ constexpr int qc_max_threads(int rule) { return rule >= SB_CN_MINSUM ? 768 : 768; }
+#ifndef SB_QC_PHI_THREADS
+#define SB_QC_PHI_THREADS 768                             // A/B hook: -DSB_QC_PHI_THREADS=1024 builds the 64-register variant
+#endif
+__host__ __device__ constexpr int qc_max_threads(int rule) { return rule == SB_CN_BOXPLUS_PHI ? SB_QC_PHI_THREADS : 768; }
 
 template <int RULE, int REP>                              // REP: copies of the phi log table (32 or 1)
 __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
