@@ -34,7 +34,9 @@ __device__ __forceinline__ void demap_qam_symbol(float2 yy, float inv_n0, const 
                 else mx0 = fmaxf(mx0, e[t]);
             }
             float l;
-            if (METHOD == 1) {
+            // H == 1 (QPSK / BPSK per dimension): each group has ONE member, logsumexp of one value is the value itself
+            // (sb_expf(0) == 1 and sb_logf(1) == 0 exactly), so "app" equals "maxlog" bit for bit without exp / log
+            if (METHOD == 1 || H == 1) {
                 l = __fsub_rn(mx1, mx0);
             } else {
                 mx0 = (mx0 > -INFINITY && mx0 < INFINITY) ? mx0 : 0.f;

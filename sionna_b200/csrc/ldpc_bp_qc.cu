@@ -476,7 +476,9 @@ __device__ __forceinline__ void vn_all(const QcParams& p, const WarpCtx& w, uint
 #endif
 __host__ __device__ constexpr int qc_max_threads(int rule) { return rule == SB_CN_BOXPLUS_PHI ? SB_QC_PHI_THREADS : 768; }
 
-template <int RULE, int REP>                              // REP: copies of the phi log table (32 or 1)
+// REP: copies of the phi log table (32, 8 or 1). EARLY: the early-termination variant (hard-decision bytes + syndrome
+// pass); a separate instantiation so that the default kernel carries none of it (as a run-time flag it cost 2 %).
+template <int RULE, int REP, bool EARLY>
 __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(const __grid_constant__ QcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
     int* unsat = reinterpret_cast<int*>(smem_raw + off_bar + 12);
     const int off_tab = off_bar + 16;                     // phi log table, tab_rep copies interleaved per entry
     // early termination: one hard-decision byte per VN behind the table
-    unsigned char* hd = p.early ? smem_raw + off_tab + (RULE == SB_CN_BOXPLUS_PHI ? REP * SB_LOGTAB_N * 8 : 0) : nullptr;
+    unsigned char* hd = EARLY ? smem_raw + off_tab + (RULE == SB_CN_BOXPLUS_PHI ? REP * SB_LOGTAB_N * 8 : 0) : nullptr;
     const uint32_t msgb = smem_u32(smem_raw);             // 32-bit shared-window addresses for the hot loops
     const uint32_t s_ce = msgb + off_ce;
     // a warp keeps one 32-lane slice `ib` of every block row/column it visits; G warp groups share the rows
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
         // writes the outputs): the outputs equal a fixed-iteration decode with num_iter = it + 1 bit for bit.
         int limit = p.num_iter;
         for (int it = 0; it < limit; ++it) {
-            if (p.early && it > 0 && it < limit - 1) {
+            if (EARLY && it > 0 && it < limit - 1) {
                 if (tid == 0) *unsat = 0;
                 __syncthreads();
                 syndrome_pass(p, w, s_row, hd, unsat);
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(qc_max_threads(RULE), 1) ldpc_bp_qc_kernel(con
             vn_all<0, true>(p, w, msgb, llr_s, s_col, s_ce, clip, final_pass, final_pass, b, hd);
             __syncthreads();
         }
-        if (p.iters_out && tid == 0) p.iters_out[b] = limit;
+        if (EARLY && p.iters_out && tid == 0) p.iters_out[b] = limit;
         if (p.state_out) {
             float* st = p.state_out + (size_t)b * p.E;
             for (int e = tid; e < p.E; e += T) st[e] = __fmul_rn(msg[p.slot_of_edge[e]], -1.f);
@@ -633,12 +635,12 @@ int qc_ensure_uploaded(sb_ldpc_graph* g) {
     return SB_OK;
 }
 
-template <int RULE>
-int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = ldpc_bp_qc_kernel<RULE, 32>;
+template <int RULE, bool EARLY>
+int launch_qc_e(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = ldpc_bp_qc_kernel<RULE, 32, EARLY>;
     if constexpr (RULE == SB_CN_BOXPLUS_PHI) {
-        if (p.tab_rep == 8) kern = ldpc_bp_qc_kernel<RULE, 8>;
-        if (p.tab_rep == 1) kern = ldpc_bp_qc_kernel<RULE, 1>;
+        if (p.tab_rep == 8) kern = ldpc_bp_qc_kernel<RULE, 8, EARLY>;
+        if (p.tab_rep == 1) kern = ldpc_bp_qc_kernel<RULE, 1, EARLY>;
     }
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -648,6 +650,11 @@ int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t sme
     kern<<<(unsigned)grid, threads, smem, stream>>>(p);
     SB_LAUNCH_CHECK();
     return SB_OK;
+}
+
+template <int RULE>
+int launch_qc(const sb_ldpc_graph* g, const QcParams& p, int threads, size_t smem, cudaStream_t stream) {
+    return p.early ? launch_qc_e<RULE, true>(g, p, threads, smem, stream) : launch_qc_e<RULE, false>(g, p, threads, smem, stream);
 }
 
 }  // namespace

@@ -308,7 +308,7 @@ def test_full_batch_4096_bit_exact_vs_oracle(cuda_device, rule):
     ref = O.LDPC5GDecoderRef(enc_r, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20)
     xr = ref(llr, math_mode=1, order="kernel", num_threads=threads)
     assert np.array_equal(x, xr)
-    blk = ((x[:, :k] > 0) != (u > 0)).any(axis=1).mean()
+    blk = ((x > 0) != (c > 0)).any(axis=1).mean()           # transmitted codeword positions
     assert 0.0 < blk < 1.0                                  # both converged and non-converged codewords are present
     if rule == "minsum":
         x2 = LDPC5GDecoder(enc, cn_update=rule, hard_out=False, return_infobits=False, num_iter=20, sum_order="reference")(
