@@ -99,23 +99,34 @@ void sbo_demap_qam(const float* y, const float* no, int64_t no_inner, const floa
                 float dd = yd - (d ? lev_im[t] : lev_re[t]);
                 e[t] = -(dd * dd) * inv_n0;
             }
+            float wgt[32], mx = -INFINITY;                         /* "app", H > 1: exponentials relative to the dimension's maximum */
+            for (int t = 0; t < L; ++t) mx = fmaxf(mx, e[t]);
+            mx = isfinite(mx) ? mx : 0.f;
+            for (int t = 0; t < L; ++t) { float a = e[t] - mx; wgt[t] = a < -87.3f ? 0.f : sb_expf(a); }
             for (int u = 0; u < H; ++u) {
                 int mask = 1 << (H - 1 - u);
                 float mx0 = -INFINITY, mx1 = -INFINITY;
                 for (int t = 0; t < L; ++t) { if (t & mask) mx1 = fmaxf(mx1, e[t]); else mx0 = fmaxf(mx0, e[t]); }
                 float l;
-                if (method == 1) {
+                if (method == 1 || H == 1) {
                     l = mx1 - mx0;
                 } else {
-                    mx0 = isfinite(mx0) ? mx0 : 0.f;
-                    mx1 = isfinite(mx1) ? mx1 : 0.f;
                     float s0 = 0.f, s1 = 0.f;
-                    for (int t = 0; t < L; ++t) {                  /* ascending t within each group */
-                        if (t & mask) s1 += sb_expf(e[t] - mx1); else s0 += sb_expf(e[t] - mx0);
+                    for (int t = 0; t < L; ++t) { if (t & mask) s1 += wgt[t]; else s0 += wgt[t]; }   /* ascending t */
+                    if (s0 > 0.f && s1 > 0.f) {
+                        l = sb_logf(s1) - sb_logf(s0);
+                    } else {                                       /* a whole group underflowed: per-group maxima */
+                        mx0 = isfinite(mx0) ? mx0 : 0.f;
+                        mx1 = isfinite(mx1) ? mx1 : 0.f;
+                        s0 = 0.f; s1 = 0.f;
+                        for (int t = 0; t < L; ++t) {
+                            if (t & mask) { float a = e[t] - mx1; s1 += a < -87.3f ? 0.f : sb_expf(a); }
+                            else { float a = e[t] - mx0; s0 += a < -87.3f ? 0.f : sb_expf(a); }
+                        }
+                        float b1 = (s1 > 0.f ? sb_logf(s1) : -INFINITY) + mx1;
+                        float b0 = (s0 > 0.f ? sb_logf(s0) : -INFINITY) + mx0;
+                        l = b1 - b0;
                     }
-                    float b1 = (s1 > 0.f ? sb_logf(s1) : -INFINITY) + mx1;
-                    float b0 = (s0 > 0.f ? sb_logf(s0) : -INFINITY) + mx0;
-                    l = b1 - b0;
                 }
                 llr[s * m + 2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
             }

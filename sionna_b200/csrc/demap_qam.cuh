@@ -25,6 +25,24 @@ __device__ __forceinline__ void demap_qam_symbol(float2 yy, float inv_n0, const 
             float dd = __fsub_rn(yd, d ? li[t] : lr[t]);
             e[t] = __fmul_rn(-__fmul_rn(dd, dd), inv_n0);
         }
+        // "app": exponentials relative to the LARGEST exponent of the dimension, evaluated once (L exps) and shared by the
+        // H bits of the dimension: LLR = log(sum_{bit=1} w_t) - log(sum_{bit=0} w_t), the maximum cancels. The reference's
+        // per-group logsumexp (mapping.py:915-918) is the same number up to rounding; it is kept as the fallback for a
+        // group whose members all underflow (e_t - max < -87.3), where the shared form would return log(0).
+        float wgt[L];
+        if (METHOD == 0 && H > 1) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < L; ++t) mx = fmaxf(mx, e[t]);
+            mx = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
+#pragma unroll
+            for (int t = 0; t < L; t += 2) {
+                float a0 = __fsub_rn(e[t], mx), a1 = __fsub_rn(e[t + 1], mx);
+                float2 r = sb_expf2_inrange(make_float2(fmaxf(a0, -87.3f), fmaxf(a1, -87.3f)));
+                wgt[t] = a0 < -87.3f ? 0.f : r.x;
+                wgt[t + 1] = a1 < -87.3f ? 0.f : r.y;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < H; ++u) {
             float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -39,26 +57,27 @@ __device__ __forceinline__ void demap_qam_symbol(float2 yy, float inv_n0, const 
             if (METHOD == 1 || H == 1) {
                 l = __fsub_rn(mx1, mx0);
             } else {
-                mx0 = (mx0 > -INFINITY && mx0 < INFINITY) ? mx0 : 0.f;
-                mx1 = (mx1 > -INFINITY && mx1 < INFINITY) ? mx1 : 0.f;
                 float s0 = 0.f, s1 = 0.f;
-                // the k-th member of group 0 and of group 1 share one packed exp
 #pragma unroll
-                for (int k = 0; k < L / 2; ++k) {
-                    const int lo = k & ((1 << (H - 1 - u)) - 1), hi = k >> (H - 1 - u);
-                    const int t0 = (hi << (H - u)) | lo, t1 = t0 | (1 << (H - 1 - u));
-                    float a0 = __fsub_rn(e[t0], mx0), a1 = __fsub_rn(e[t1], mx1);
-                    float2 r = sb_expf2_inrange(make_float2(fmaxf(a0, -87.3f), fmaxf(a1, -87.3f)));
-                    if (a0 < -87.3f) r.x = 0.f;
-                    if (a1 < -87.3f) r.y = 0.f;
-                    s0 = __fadd_rn(s0, r.x);
-                    s1 = __fadd_rn(s1, r.y);
+                for (int t = 0; t < L; ++t) {                       // ascending t inside each group
+                    if ((t >> (H - 1 - u)) & 1) s1 = __fadd_rn(s1, wgt[t]);
+                    else s0 = __fadd_rn(s0, wgt[t]);
                 }
-                // both logs in one packed evaluation (sb_logf2 is bit-identical to sb_logf per element)
-                const float2 lg = sb_logf2(make_float2(fmaxf(s0, 1.17549435e-38f), fmaxf(s1, 1.17549435e-38f)));
-                float b1 = __fadd_rn(s1 > 0.f ? lg.y : -INFINITY, mx1);
-                float b0 = __fadd_rn(s0 > 0.f ? lg.x : -INFINITY, mx0);
-                l = __fsub_rn(b1, b0);
+                if (s0 > 0.f && s1 > 0.f) {
+                    const float2 lg = sb_logf2(make_float2(s0, s1));
+                    l = __fsub_rn(lg.y, lg.x);
+                } else {                                            // a whole group underflowed: per-group maxima
+                    mx0 = (mx0 > -INFINITY && mx0 < INFINITY) ? mx0 : 0.f;
+                    mx1 = (mx1 > -INFINITY && mx1 < INFINITY) ? mx1 : 0.f;
+                    s0 = 0.f; s1 = 0.f;
+                    for (int t = 0; t < L; ++t) {
+                        if ((t >> (H - 1 - u)) & 1) { float a = __fsub_rn(e[t], mx1); s1 = __fadd_rn(s1, a < -87.3f ? 0.f : sb_expf(a)); }
+                        else { float a = __fsub_rn(e[t], mx0); s0 = __fadd_rn(s0, a < -87.3f ? 0.f : sb_expf(a)); }
+                    }
+                    float b1 = __fadd_rn(s1 > 0.f ? sb_logf(s1) : -INFINITY, mx1);
+                    float b0 = __fadd_rn(s0 > 0.f ? sb_logf(s0) : -INFINITY, mx0);
+                    l = __fsub_rn(b1, b0);
+                }
             }
             out[2 * u + d] = hard_out ? (l > 0.f ? 1.f : 0.f) : l;
         }

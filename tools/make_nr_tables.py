@@ -7,7 +7,8 @@ sionna_b200/phy/nr/codes/nr_tables.npz (run in the build container, /root/refere
     (PUSCHConfig.precoding_matrix, /root/reference/src/sionna/phy/nr/pusch_config.py:597-807)
 
 Only numbers are stored. The reference cannot be imported (TensorFlow is absent), so the two code fragments are
-located with `ast` and evaluated in isolation.
+located with `ast`: the MCS lists go through a numbers-and-arithmetic-only evaluator; the codebook function is vetted node by node
+(NumPy arithmetic only) and executed with a five-name builtins table.
 """
 import ast
 import os
@@ -16,6 +17,27 @@ import numpy as np
 
 REF = "/root/reference/src/sionna/phy/nr"
 OUT = os.path.join(os.path.dirname(__file__), "..", "sionna_b200", "phy", "nr", "codes", "nr_tables.npz")
+
+
+def _num_eval(node):
+    """Evaluates a tree of numbers, lists / tuples and + - * / only (what the MCS tables are written with)."""
+    if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
+        return node.value
+    if isinstance(node, (ast.List, ast.Tuple)):
+        return [_num_eval(e) for e in node.elts]
+    if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+        v = _num_eval(node.operand)
+        return -v if isinstance(node.op, ast.USub) else v
+    if isinstance(node, ast.BinOp) and isinstance(node.op, (ast.Add, ast.Sub, ast.Mult, ast.Div)):
+        a, b = _num_eval(node.left), _num_eval(node.right)
+        if isinstance(node.op, ast.Add):
+            return a + b                                        # numbers, or list concatenation
+        if isinstance(node.op, ast.Mult):
+            return a * b                                        # numbers, or list repetition
+        if isinstance(a, list) or isinstance(b, list):
+            raise ValueError("list operand of - or /")
+        return a - b if isinstance(node.op, ast.Sub) else a / b
+    raise ValueError("unexpected node in a numeric table: " + ast.dump(node)[:80])
 
 
 def literal_lists(path, func, names):
@@ -27,7 +49,7 @@ def literal_lists(path, func, names):
                 if isinstance(st, ast.Assign) and isinstance(st.targets[0], ast.Name) and st.targets[0].id in names:
                     call = st.value                          # tf.convert_to_tensor([...])
                     arg = call.args[0] if isinstance(call, ast.Call) else call
-                    out[st.targets[0].id] = eval(compile(ast.Expression(arg), "<mcs>", "eval"), {})
+                    out[st.targets[0].id] = _num_eval(arg)             # nested number lists with simple arithmetic: nothing is executed
     return out
 
 
@@ -38,8 +60,23 @@ def precoding_tables(path):
         if isinstance(node, ast.FunctionDef) and node.name == "precoding_matrix":
             fn = node
     fn.decorator_list = []
+    # The codebooks are written as NumPy expressions (np.array([...]) / np.sqrt(2), 1j factors), not literals, so this one
+    # function body is executed - after checking that it contains nothing but arithmetic on `np` and `self` attributes
+    # (no imports, no calls other than np.* / complex / float / int / len / range, no attribute access on anything else)
+    # and with only those five builtins.
+    for node in ast.walk(fn):
+        if isinstance(node, (ast.Import, ast.ImportFrom, ast.Global, ast.Nonlocal, ast.Lambda, ast.With, ast.Try)):
+            raise RuntimeError("unexpected construct in the reference's precoding_matrix")
+        if isinstance(node, ast.Call):
+            f = node.func
+            ok = (isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "np") or \
+                 (isinstance(f, ast.Name) and f.id in ("complex", "float", "int", "len", "range"))
+            if not ok:
+                raise RuntimeError("unexpected call in the reference's precoding_matrix")
+        if isinstance(node, ast.Attribute) and not (isinstance(node.value, ast.Name) and node.value.id in ("np", "self")):
+            raise RuntimeError("unexpected attribute access in the reference's precoding_matrix")
     mod = ast.Module(body=[fn], type_ignores=[])
-    ns = {"np": np}
+    ns = {"np": np, "__builtins__": {"complex": complex, "float": float, "int": int, "len": len, "range": range}}
     exec(compile(mod, "<w>", "exec"), ns)
     tabs = {}
     for layers, ports, count in ((1, 2, 6), (1, 4, 28), (2, 2, 3), (2, 4, 22), (3, 4, 7), (4, 4, 5)):
