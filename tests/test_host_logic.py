@@ -318,3 +318,45 @@ def test_frontend_tables_reproduce_ls_plus_interpolation(interp, streams):
     e_sum = np.maximum(er[0, 0, 0].reshape(streams, -1), 0).sum(0)
     assert np.allclose(t["e_sum"], e_sum, rtol=1e-6)
     assert np.array_equal(t["re_full"], (np.arange(14)[:, None] * 76 + eff[None, :]).reshape(-1))
+
+
+@pytest.mark.parametrize("layers,ports,length,addpos,cdm,interp", [(2, 2, 1, 1, 2, "lin"), (1, 1, 2, 1, 2, "lin"),
+                                                                     (4, 4, 1, 0, 2, "nn"), (2, 4, 2, 0, 1, "lin")])
+def test_frontend_tables_pusch_cdm_despreading(layers, ports, length, addpos, cdm, interp):
+    """PUSCH: the fused front-end's tables also fold the CDM de-spreading of PUSCHLSChannelEstimator
+    (nr/pusch_channel_estimation.py:131-167) between the LS division and the interpolation; checked against the oracle
+    chain ls_estimate -> pusch_ls_combine -> interpolation on random received grids."""
+    from sionna_b200.phy.nr import PUSCHConfig, PUSCHTransmitter
+    from sionna_b200.phy.nr.pusch_channel_estimation import PUSCHLSChannelEstimator
+    from sionna_b200.phy.ofdm import frontend_tables
+    from oracle import ofdm as F
+    from oracle import nr as ON
+    kw = dict(precoding="codebook", tpmi=1) if ports > layers else {}
+    pc = PUSCHConfig(num_layers=layers, num_antenna_ports=ports, **kw)
+    pc.carrier.n_size_grid = 4
+    pc.dmrs.length = length
+    pc.dmrs.additional_position = addpos
+    pc.dmrs.num_cdm_groups_without_data = cdm
+    tx = PUSCHTransmitter(pc)
+    rg = tx.resource_grid
+    est = PUSCHLSChannelEstimator(rg, tx._dmrs_length, tx._dmrs_additional_position, tx._num_cdm_groups_without_data,
+                                  interpolation_type=interp)
+    t = frontend_tables(rg, est)
+    assert t is not None and t["num_terms"] <= 16
+    rng = np.random.default_rng(9)
+    s_n, nf = rg.num_ofdm_symbols, rg.fft_size
+    y = rng.normal(size=(2, 1, 2, s_n, nf)) + 1j * rng.normal(size=(2, 1, 2, s_n, nf))
+    eff = np.asarray(rg.effective_subcarrier_ind)
+    mask, pil = rg.pilot_pattern.mask.astype(bool), rg.pilot_pattern.pilots
+    h, err = F.ls_estimate(y[..., eff], mask, pil, 1.0)
+    h, err = ON.pusch_ls_combine(h, err, est._num_dmrs_syms, est._dmrs_length, est._num_cdm_groups_without_data)
+    if interp == "nn":
+        hr, er = F.nn_interp(h, mask, pil), F.nn_interp(err, mask, pil)
+    else:
+        hr, er = F.lin_interp(h, mask, pil), F.lin_interp(err, mask, pil).real
+    ts = hr.shape[3] * hr.shape[4]
+    yf = y.reshape(2, 1, 2, -1)
+    idx, w = t["t_idx"], t["t_w"].astype(np.complex128)
+    got = np.where(idx >= 0, w * yf[..., np.maximum(idx, 0)], 0).sum(-1)
+    assert np.allclose(got, hr.reshape(2, 1, 2, ts, -1), atol=2e-6)
+    assert np.allclose(t["e_sum"], np.maximum(er[0, 0, 0].reshape(ts, -1), 0).sum(0), rtol=1e-6)
