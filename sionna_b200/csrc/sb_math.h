@@ -10,9 +10,10 @@
 // "libm" mode (glibc expf/logf) measures how far any <=1 ulp libm -- such as the
 // TensorFlow/Eigen one the reference runs on -- sits from it.
 //
-// Accuracy (measured exhaustively by tests/test_sb_math.py against float64):
-//   sb_expf : <= 0.87 ulp on [-87.3, 88.7]
-//   sb_logf : <= 0.93 ulp on all positive normal floats
+// Accuracy (tools/check_math.c against float64: exhaustive over all floats when run by hand, a stride of 997 in
+// tests/test_sb_math.py):
+//   sb_expf : <= 0.99 ulp on [-87.3, 88.7]          (exhaustive: 0.9876)
+//   sb_logf : <= 0.87 ulp on all positive normal floats  (exhaustive: 0.8623; sb_tanhf 1.509, sb_atanhf 2.768, sb_logf_tab 0.977)
 // Both are exact at the two points the reference's phi clipping constants rely on:
 //   sb_expf(8.5e-8f) == 1+2^-23   and   sb_logf(2^24) == sb_logf(2^24-1).
 #pragma once

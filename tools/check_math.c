@@ -5,13 +5,16 @@
 #include <float.h>
 #include "../sionna_b200/csrc/sb_math.h"
 static double ulp_of(double ref) { float f = (float)ref; if (f == 0) return FLT_MIN; int e; frexpf(fabsf(f), &e); return ldexp(1.0, e - 24); }
-int main(void) {
+// usage: check_math [stride]   stride 1 = every float (about 100 s on 8 cores); tests/test_sb_math.py runs a stride of
+// 997 (prime: every exponent and a spread of mantissas) and asserts the bounds sb_math.h states.
+int main(int argc, char** argv) {
+    const long long stride = argc > 1 ? atoll(argv[1]) : 1;
     double worst_exp = 0, worst_log = 0, worst_tanh = 0, worst_atanh = 0; float wx = 0, wl = 0, wt = 0, wa = 0;
     #pragma omp parallel
     {
         double we = 0, wlg = 0, wth = 0, wat = 0; float xe = 0, xl = 0, xt = 0, xa = 0;
         #pragma omp for schedule(static)
-        for (long long i = 0; i < (1LL << 32); ++i) {
+        for (long long i = 0; i < (1LL << 32); i += stride) {
             uint32_t u = (uint32_t)i; float x; memcpy(&x, &u, 4);
             if (!(x == x) || isinf(x)) continue;
             if (x >= -87.3f && x <= 88.7f) {
@@ -45,7 +48,7 @@ int main(void) {
         {
             double w_ = 0; float x_ = 0; long long ng = 0, nm = 0; float xn = 0;
             #pragma omp for schedule(static)
-            for (long long i = 0x00800000LL; i < 0x7f800000LL; ++i) {
+            for (long long i = 0x00800000LL; i < 0x7f800000LL; i += stride) {
                 uint32_t u = (uint32_t)i; float y; memcpy(&y, &u, 4);
                 double ref = log((double)y);
                 // y >= 1: error in ulps of the result; y < 1: absolute error in units of 2^-24 (what phi needs)
