@@ -621,7 +621,7 @@ __global__ void mimo_linalg_kernel(int mode, const float2* __restrict__ y, const
                                    long long R, int M, int K) {
     extern __shared__ float2 smem[];
     const int T = blockDim.x, t = threadIdx.x;
-    const int N = (mode == 2 && s == nullptr) ? K : M;             // order of the matrix that is factorised
+    const bool rx_side = !(mode == 2 && s == nullptr);             // factorise the M x M receive-side matrix (else K x K)
     Scratch A{smem, T, t}, H{smem + (size_t)M * M * T, T, t}, X{smem + (size_t)(M * M + M * K) * T, T, t};
     for (long long r = (long long)blockIdx.x * T + t; r < R; r += (long long)gridDim.x * T) {
         if (h) for (int e = 0; e < M * K; ++e) H(e) = h[r * M * K + e];
@@ -656,7 +656,7 @@ __global__ void mimo_linalg_kernel(int mode, const float2* __restrict__ y, const
             continue;
         }
         // modes 2, 3: G
-        if (N == M) {                                               // G^H = (H H^H + S)^-1 H, column by column
+        if (rx_side) {                                              // G^H = (H H^H + S)^-1 H, column by column
             for (int a = 0; a < M; ++a)
                 for (int b = 0; b <= a; ++b) {
                     float2 acc = s[r * M * M + a * M + b];
@@ -683,7 +683,7 @@ __global__ void mimo_linalg_kernel(int mode, const float2* __restrict__ y, const
             for (int k = 0; k < K; ++k)
                 for (int m = 0; m < M; ++m) {
                     float2 g = X(k * M + m);
-                    if (N == M) { g = X(m * K + k); g.y = -g.y; }                  // G = (G^H)^H
+                    if (rx_side) { g = X(m * K + k); g.y = -g.y; }                 // G = (G^H)^H
                     out0[(r * K + k) * M + m] = g;
                 }
         } else {

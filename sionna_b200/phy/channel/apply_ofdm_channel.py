@@ -21,6 +21,9 @@ class ApplyOFDMChannel(Block):
         x = x.to(device=dev, dtype=torch.complex64).contiguous()
         h = h_freq.to(device=dev, dtype=torch.complex64).contiguous()
         b, rx, ra, tx, ta, s_, f_ = h.shape
+        if tuple(x.shape) != (b, tx, ta, s_, f_):
+            raise ValueError(f"x of shape {tuple(x.shape)} does not match h_freq of shape {tuple(h.shape)} "
+                             "([batch, num_rx, num_rx_ant, num_tx, num_tx_ant, num_ofdm_symbols, fft_size])")
         y = torch.empty((b, rx, ra, s_, f_), dtype=torch.complex64, device=dev)
         no_t, inner, add = None, 1, 0
         seed, off = 0, 0
