@@ -342,16 +342,20 @@ int sb_ofdm_lmmse(const float* d_y, const float* d_h_hat, const float* d_err_var
  * linear interpolation + OFDM equaliser glue + LMMSE equalisation + square-QAM demapping in ONE launch, for receivers
  * without interfering streams and 1..4 streams (ofdm/channel_estimation.py:138-285, 364-734, ofdm/equalization.py:126-275,
  * mimo/equalization.py:101-233, mapping.py:664-691, 927-967). The estimator is linear in the received pilots, so the host
- * passes it as tables: h_hat[ant, q](re) = sum_i t_w[q, re, i] * y[ant, t_idx[q, re, i]] (t_idx = position in the FULL
- * grid, -1 ends the list), err_var[ant, q](re) = no[ant] * E[q, re], d_e_sum[re] = sum_q max(E[q, re], 0).
+ * passes it as tables over a LIST of num_re resource elements (normally the data-carrying ones; pilot-only symbols need
+ * not be listed): h_hat[ant, q](re) = sum_i t_w[q, i, re] * y[ant, t_idx[q, i, re]]  (term-major [num_tx_streams,
+ * num_terms <= 16, num_re]; t_idx = position in the FULL grid, -1 ends the list), err_var[ant, q](re) = no[ant] * E[q, re],
+ * d_e_sum[re] = sum_q max(E[q, re], 0).
  *   d_y [batch, num_rx, num_rx_ant, grid_size] full resource grid (num_ofdm_symbols * fft_size), d_re_full[num_re]:
- *   full-grid position of every effective RE; d_no / h_no_stride, d_desired, d_out_stream, d_data_pos as sb_ofdm_lmmse.
+ *   full-grid position of every listed RE; d_data_pos [num_tx_streams, num_re]; d_no / h_no_stride, d_desired,
+ *   d_out_stream as sb_ofdm_lmmse; h_lev_re / h_lev_im: HOST arrays of the 2^bits_per_dim PAM levels by label (they
+ *   travel as kernel parameters).
  *   Outputs: d_llr [batch, num_tx_streams, num_data * 2 * bits_per_dim] (method 0 app / 1 maxlog, levels as sb_demap_qam)
  *   and / or d_x_hat, d_no_eff [batch, num_tx_streams, num_data]; either may be NULL. */
 int sb_ofdm_frontend(const float* d_y, const float* d_no, const int64_t* h_no_stride, const int32_t* d_desired,
                      const int32_t* d_out_stream, const int32_t* d_data_pos, const int32_t* d_re_full,
-                     const int32_t* d_t_idx, const float* d_t_w, const float* d_e_sum, const float* d_lev_re,
-                     const float* d_lev_im, float* d_llr, float* d_x_hat, float* d_no_eff, int64_t batch, int32_t num_rx,
+                     const int32_t* d_t_idx, const float* d_t_w, const float* d_e_sum, const float* h_lev_re,
+                     const float* h_lev_im, float* d_llr, float* d_x_hat, float* d_no_eff, int64_t batch, int32_t num_rx,
                      int32_t num_rx_ant, int32_t num_tx_streams, int32_t num_re, int32_t grid_size, int32_t streams_per_rx,
                      int32_t num_terms, int32_t num_data, int32_t bits_per_dim, int32_t method, int32_t hard_out,
                      void* stream);

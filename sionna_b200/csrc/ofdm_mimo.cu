@@ -180,56 +180,134 @@ __global__ void ofdm_demod_kernel(const float2* __restrict__ x, float2* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// FFT sizes up to 1024 (every OFDM grid up to 85 PRB, e.g. 72, 76, 128, 180, 600): one WARP per transform, several
-// transforms per CTA, no CTA-wide barrier in the loop. A stage of radix p computes each of the N outputs as a p-term
-// DFT sum (lanes stride over the outputs); all index arithmetic of the Stockham permutation comes from per-stage tables
-// built on the host (input base, twiddle index, root step: 3 x uint16 per output), so the inner loop is
-// 2 shared loads + 1 complex multiply-add.
+// FFT sizes up to 1024 (every OFDM grid up to 85 PRB, e.g. 72, 76, 128, 180, 600): one WARP per FPW transforms, several
+// warps per CTA, no CTA-wide barrier in the loop. Stockham stages; a lane owns a whole radix-p BUTTERFLY (inputs in
+// registers), the FPW * N/p butterflies of a stage are dealt over the lanes:
+//   p = 2, 4      the usual add / subtract networks;
+//   odd p <= 19   (3, 5, 7, 11, 13, 17, 19: the 76-point grid is 4 * 19) real-symmetric form of the p-point DFT: with
+//                 a_r = x_r + x_(p-r), b_r = x_r - x_(p-r) the outputs c and p - c are E_c +- O_c,
+//                 E_c = x_0 + sum_r a_r cos(2 pi r c / p), O_c = -j sum_r b_r sin(2 pi r c / p): (p-1)^2 real FMAs per
+//                 butterfly instead of 4 p (p-1), the roots are warp-uniform (broadcast) shared-memory loads;
+//   other p       direct p-term sums.
+// The largest prime comes last in the plan, where the Stockham twiddles are all 1 (k = 0) and are skipped.
 // ---------------------------------------------------------------------------------------------------------------
 struct SmallFftPlan {
     int n, n_stages;
-    int p[12], rstride[12];
-    const unsigned short* tab;       // [n_stages][3][n]: in_base, twiddle index, root step
+    int p[12];
+    unsigned mg_nb[12], mg_span[12];   // ceil(2^32 / (n / p)), ceil(2^32 / span): exact quotients for indices < 4096
+    float2 roots[75];                  // exp(-2 pi i j / P), j < P, for P = 3, 5, 7, 11, 13, 17, 19 (root_offset(P))
 };
 
-// FPW transforms per warp at a time: a lane owns output o of all FPW transforms, so the stage tables and the roots
-// W[widx] are loaded once per FPW complex multiply-adds. Buffers: x / y [FPW][N].
+__host__ __device__ constexpr int root_offset(int P) {
+    return P == 3 ? 0 : P == 5 ? 3 : P == 7 ? 8 : P == 11 ? 15 : P == 13 ? 26 : P == 17 ? 39 : 56;
+}
+
+// one butterfly of odd prime radix P: inputs xi[r * rs], outputs yo[c * os] * W[c * tws]. The P-th roots are kernel
+// parameters, and every index (r * c mod P) is a compile-time constant: the FMAs take them straight from the constant
+// bank (no loads, no index arithmetic).
+template <int P>
+__device__ __forceinline__ void fft_butterfly_odd(const float2* xi, int rs, float2* yo, int os, const SmallFftPlan& plan,
+                                                  const float2* __restrict__ W, int tws) {
+    constexpr int HP = (P - 1) / 2, RO = root_offset(P);
+    const float2 x0 = xi[0];
+    float2 a[HP], b[HP];
+    float2 s0 = x0;
+#pragma unroll
+    for (int r = 0; r < HP; ++r) {
+        const float2 u = xi[(r + 1) * rs], v = xi[(P - 1 - r) * rs];
+        a[r] = cadd(u, v);
+        b[r] = csub(u, v);
+        s0 = cadd(s0, a[r]);
+    }
+    yo[0] = s0;
+#pragma unroll
+    for (int c = 1; c <= HP; ++c) {
+        float2 E = x0, O = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < HP; ++r) {
+            const float2 w = plan.roots[RO + ((r + 1) * c) % P];   // (cos t, -sin t), t = 2 pi (r + 1) c / P
+            E.x = fmaf(a[r].x, w.x, E.x);
+            E.y = fmaf(a[r].y, w.x, E.y);
+            O.x = fmaf(-b[r].y, w.y, O.x);                          // -j b sin t
+            O.y = fmaf(b[r].x, w.y, O.y);
+        }
+        float2 xc = cadd(E, O), xpc = csub(E, O);
+        if (tws) {
+            xc = cmul(xc, W[c * tws]);
+            xpc = cmul(xpc, W[(P - c) * tws]);
+        }
+        yo[c * os] = xc;
+        yo[(P - c) * os] = xpc;
+    }
+}
+
+// FPW transforms per warp at a time. Buffers: x / y [FPW][N].
 template <int FPW>
 __device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const float2* __restrict__ W,
-                                                  const unsigned short* __restrict__ tab, const SmallFftPlan& plan, int lane) {
+                                                  const SmallFftPlan& plan, int lane) {
     const int N = plan.n;
+    int span = 1, cur = N;
     for (int st = 0; st < plan.n_stages; ++st) {
-        const int p = plan.p[st], rs = plan.rstride[st];
-        const unsigned short* t_in = tab + (size_t)st * 3 * N;
-        const unsigned short* t_tw = t_in + N;
-        const unsigned short* t_cs = t_tw + N;
-        for (int o = lane; o < N; o += 32) {
-            const int in = t_in[o], cs = t_cs[o];
-            float2 acc[FPW];
-#pragma unroll
-            for (int f = 0; f < FPW; ++f) acc[f] = x[f * N + in];  // r = 0: root index 0 -> W = 1
-            int widx = cs;
-            for (int r = 1; r < p; ++r) {
-                const float2 w = W[widx];
-                const float2* xp = x + in + r * rs;
-#pragma unroll
-                for (int f = 0; f < FPW; ++f) acc[f] = cadd(acc[f], cmul(xp[f * N], w));
-                widx += cs;
-                if (widx >= N) widx -= N;
+        const int p = plan.p[st], m = cur / p, rs = span * m;
+        const int nb = N / p;                                      // butterflies per transform: b = q + span * k
+        const unsigned mg_nb = plan.mg_nb[st], mg_span = plan.mg_span[st];
+        for (int i = lane; i < FPW * nb; i += 32) {
+            const int f = nb == 1 ? i : (int)__umulhi((unsigned)i, mg_nb), bb = i - f * nb;
+            const int k = span == 1 ? bb : (int)__umulhi((unsigned)bb, mg_span), q = bb - k * span;
+            const float2* xi = x + f * N + q + span * k;
+            float2* yo = y + f * N + q + span * p * k;
+            const int tws = k * span;                              // root index step of the Stockham twiddle (c * tws < N)
+            switch (p) {
+                case 2: {
+                    const float2 a0 = xi[0], a1 = xi[rs];
+                    yo[0] = cadd(a0, a1);
+                    yo[span] = cmul(csub(a0, a1), W[tws]);
+                    break;
+                }
+                case 4: {
+                    const float2 a0 = xi[0], a1 = xi[rs], a2 = xi[2 * rs], a3 = xi[3 * rs];
+                    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+                    const float2 t3j = make_float2(t3.y, -t3.x);   // -j * t3
+                    yo[0] = cadd(t0, t2);
+                    yo[span] = cmul(cadd(t1, t3j), W[tws]);
+                    yo[2 * span] = cmul(csub(t0, t2), W[2 * tws]);
+                    yo[3 * span] = cmul(csub(t1, t3j), W[3 * tws]);
+                    break;
+                }
+                case 3: fft_butterfly_odd<3>(xi, rs, yo, span, plan, W, tws); break;
+                case 5: fft_butterfly_odd<5>(xi, rs, yo, span, plan, W, tws); break;
+                case 7: fft_butterfly_odd<7>(xi, rs, yo, span, plan, W, tws); break;
+                case 11: fft_butterfly_odd<11>(xi, rs, yo, span, plan, W, tws); break;
+                case 13: fft_butterfly_odd<13>(xi, rs, yo, span, plan, W, tws); break;
+                case 17: fft_butterfly_odd<17>(xi, rs, yo, span, plan, W, tws); break;
+                case 19: fft_butterfly_odd<19>(xi, rs, yo, span, plan, W, tws); break;
+                default: {                                         // larger primes: direct p-term sums
+                    const int wstep = N / p;
+                    for (int c = 0; c < p; ++c) {
+                        float2 acc = xi[0];
+                        int widx = 0;
+                        for (int r = 1; r < p; ++r) {
+                            widx += c * wstep;
+                            widx -= widx >= N ? N : 0;
+                            acc = cadd(acc, cmul(xi[r * rs], W[widx]));
+                        }
+                        yo[c * span] = cmul(acc, W[c * tws]);
+                    }
+                }
             }
-            const float2 tw = W[t_tw[o]];
-#pragma unroll
-            for (int f = 0; f < FPW; ++f) y[f * N + o] = cmul(acc[f], tw);
         }
         __syncwarp();
         float2* t = x; x = y; y = t;
+        cur = m;
+        span *= p;
     }
     return x;
 }
 
 template <int DEMOD, int FPW>
-__global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __restrict__ x, float2* __restrict__ out,
-                                                             SmallFftPlan plan, int nsym, const int* __restrict__ cp,
+__global__ void __launch_bounds__(256, 2) ofdm_fft_small_kernel(const float2* __restrict__ x, float2* __restrict__ out,
+                                                             const __grid_constant__ SmallFftPlan plan, int nsym,
+                                                             const int* __restrict__ cp,
                                                              const int* __restrict__ off, int len, int l_min,
                                                              long long rows, int shift) {
     extern __shared__ float2 sm[];
@@ -237,7 +315,6 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
     float2* W = sm;
     float2* PC = sm + N;                                           // phase compensation (demodulator only)
     float2* bufs = sm + (DEMOD ? 2 : 1) * N;
-    unsigned short* tab = reinterpret_cast<unsigned short*>(bufs + (size_t)2 * FPW * N * nwarps);
     for (int k = tid; k < N; k += blockDim.x) {
         float sn, cs;
         sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
@@ -247,7 +324,6 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
             PC[k] = make_float2(cosf(tmp), sinf(tmp));
         }
     }
-    for (int i = tid; i < plan.n_stages * 3 * N; i += blockDim.x) tab[i] = plan.tab[i];
     __syncthreads();
     float2* b0 = bufs + (size_t)2 * FPW * N * warp;
     float2* b1 = b0 + (size_t)FPW * N;
@@ -275,7 +351,7 @@ __global__ void __launch_bounds__(256) ofdm_fft_small_kernel(const float2* __res
             }
         }
         __syncwarp();
-        const float2* res = fft_small_warp<FPW>(b0, b1, W, tab, plan, lane);
+        const float2* res = fft_small_warp<FPW>(b0, b1, W, plan, lane);
 #pragma unroll
         for (int f = 0; f < FPW; ++f) {
             const long long job = jb + f;
@@ -882,42 +958,27 @@ int make_plan(int n, FftPlan* plan) {
 }  // namespace
 
 namespace {
-// Host side of the small-FFT path: stage tables per size, built once and kept on the device.
-struct SmallPlanEntry { SmallFftPlan plan; };
-std::mutex g_small_plan_mutex;
-std::map<std::pair<int, int>, SmallPlanEntry> g_small_plans;   // (device, fft size): the table lives on that device
-
+// Host side of the small-FFT path: the stage radices (the plan travels as a kernel parameter).
 int get_small_plan(int n, SmallFftPlan* out) {
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_small_plan_mutex);
-    auto it = g_small_plans.find({dev, n});
-    if (it != g_small_plans.end()) { *out = it->second.plan; return SB_OK; }
     FftPlan fp;
     if (make_plan(n, &fp) != 0 || fp.n_radix > 12) { sb_set_error("fft size %d has too many factors", n); return SB_EUNSUPPORTED; }
     SmallFftPlan sp{};
     sp.n = n;
     sp.n_stages = fp.n_radix;
-    std::vector<unsigned short> tab((size_t)fp.n_radix * 3 * n);
-    int cur = n, span = 1;
+    int span = 1;
     for (int st = 0; st < fp.n_radix; ++st) {
-        const int p = fp.radix[st], m = cur / p;
-        sp.p[st] = p;
-        sp.rstride[st] = span * m;
-        for (int o = 0; o < n; ++o) {                              // output o = q + span * (p * k + c)
-            const int q = o % span, t = o / span, c = t % p, k = t / p;
-            tab[((size_t)st * 3 + 0) * n + o] = (unsigned short)(q + span * k);
-            tab[((size_t)st * 3 + 1) * n + o] = (unsigned short)(((long long)c * k * span) % n);
-            tab[((size_t)st * 3 + 2) * n + o] = (unsigned short)(((long long)c * (n / p)) % n);
-        }
-        cur = m;
-        span *= p;
+        sp.p[st] = fp.radix[st];
+        const unsigned nb = (unsigned)(n / sp.p[st]);                  // divisor 1 is special-cased in the kernel
+        sp.mg_nb[st] = nb == 1 ? 0u : (unsigned)(((1ull << 32) + nb - 1) / nb);
+        sp.mg_span[st] = span == 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)span - 1) / (unsigned)span);
+        span *= sp.p[st];
     }
-    unsigned short* d = nullptr;
-    SB_CUDA(cudaMalloc((void**)&d, tab.size() * sizeof(unsigned short)));
-    SB_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    sp.tab = d;
-    g_small_plans[{dev, n}] = SmallPlanEntry{sp};
+    const int primes[7] = {3, 5, 7, 11, 13, 17, 19};
+    for (int P : primes)
+        for (int j = 0; j < P; ++j) {
+            const double t = -2.0 * 3.14159265358979323846 * (double)j / (double)P;
+            sp.roots[root_offset(P) + j] = make_float2((float)cos(t), (float)sin(t));
+        }
     *out = sp;
     return SB_OK;
 }
@@ -928,8 +989,7 @@ template <int DEMOD, int FPW>
 int launch_fft_small_fpw(const SmallFftPlan& sp, const float2* x, float2* out, int nsym, const int* cp, const int* off,
                          int len, int l_min, long long rows, int shift, cudaStream_t stream) {
     const int warps = 8, n = sp.n;
-    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * FPW * warps) +
-                  sizeof(unsigned short) * 3 * (size_t)n * sp.n_stages;
+    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * FPW * warps);
     auto kern = ofdm_fft_small_kernel<DEMOD, FPW>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;

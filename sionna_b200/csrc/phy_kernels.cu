@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) demap_qam_kernel(const float2* __restrict
         if (s < n_sym) {
             const float2 yy = y[s];
             const float inv_n0 = __fdiv_rn(1.0f, fmaxf(no[s / no_inner], tiny));   // one division per symbol
-            demap_qam_symbol<METHOD, H>(yy, inv_n0, lr, li, hard_out, out);
+            demap_qam_symbol<METHOD, H>(yy, inv_n0, lr, li, lev_re, lev_im, hard_out, out);
         }
         // stage the warp's 32 x M LLRs through its own shared-memory tile: contiguous global stores, no CTA barrier
         {

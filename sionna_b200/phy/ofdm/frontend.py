@@ -168,8 +168,16 @@ class FusedLSLinearDetector(Block):
         if tabs is None:
             raise ValueError("FusedLSLinearDetector: this estimator / pilot pattern cannot be fused")
         des, _, out_ts, data_pos = _sm_tables(resource_grid, stream_management)
-        self._np = dict(tabs, des=des, out_ts=out_ts, data_pos=data_pos, lev_re=np.asarray(lev[0], np.float32),
-                        lev_im=np.asarray(lev[1], np.float32))
+        # Device layout: only the REs that carry data for at least one stream are listed (pilot-only OFDM symbols are not
+        # walked), and the term tables are term-major [streams, terms, listed REs] so that a warp's table loads coalesce.
+        data_pos = np.asarray(data_pos)
+        keep = np.nonzero((data_pos >= 0).any(0))[0]
+        self._np = dict(des=des, out_ts=out_ts, data_pos=np.ascontiguousarray(data_pos[:, keep]),
+                        re_full=np.ascontiguousarray(tabs["re_full"][keep]), e_sum=np.ascontiguousarray(tabs["e_sum"][keep]),
+                        t_idx=np.ascontiguousarray(tabs["t_idx"][:, keep, :].transpose(0, 2, 1)),
+                        t_w=np.ascontiguousarray(tabs["t_w"][:, keep, :].transpose(0, 2, 1)))
+        self._num_listed, self._num_terms = int(len(keep)), int(tabs["num_terms"])
+        self._lev = (np.ascontiguousarray(lev[0], np.float32), np.ascontiguousarray(lev[1], np.float32))   # host arrays
         self._dev = None
 
     def _tables(self, dev):
@@ -201,10 +209,9 @@ class FusedLSLinearDetector(Block):
             ne = torch.zeros((b, sm.num_tx, sm.num_streams_per_tx, nd), dtype=torch.float32, device=dev)
         no_arr = np.asarray(no_st, np.int64)
         check(lib().sb_ofdm_frontend(ptr(y), ptr(no_t), ptr(no_arr), ptr(t["des"]), ptr(t["out_ts"]), ptr(t["data_pos"]),
-                                     ptr(t["re_full"]), ptr(t["t_idx"]), ptr(t["t_w"]), ptr(t["e_sum"]), ptr(t["lev_re"]),
-                                     ptr(t["lev_im"]), ptr(llr), ptr(xh), ptr(ne), b, rx, ant, txs,
-                                     rg.num_ofdm_symbols * rg.num_effective_subcarriers, s_ * nf, sm.num_streams_per_rx,
-                                     int(self._np["num_terms"]), nd, m // 2, self._method, int(self._hard_out),
+                                     ptr(t["re_full"]), ptr(t["t_idx"]), ptr(t["t_w"]), ptr(t["e_sum"]), ptr(self._lev[0]),
+                                     ptr(self._lev[1]), ptr(llr), ptr(xh), ptr(ne), b, rx, ant, txs,
+                                     self._num_listed, s_ * nf, sm.num_streams_per_rx, self._num_terms, nd, m // 2, self._method, int(self._hard_out),
                                      current_stream()), "sb_ofdm_frontend")
         return llr if want_llr else (xh, ne)
 

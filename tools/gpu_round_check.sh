@@ -17,13 +17,17 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 500 --csv --l
 # full captures of the kernels the round worked on
 cap() {  # name kernel-regex command...
   n=$1; k=$2; shift 2
-  ncu --set full --clock-control none --import-source on -k "regex:$k" -s 2 -c 1 -f -o gpurun_out/${R}_$n "$@" > /dev/null 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:$k" -s ${SKIP:-2} -c 1 -f -o gpurun_out/${R}_$n "$@" > /dev/null 2>&1
 }
 cap ldpc_bp_phi ldpc_bp_qc_kernel python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-links --no-variants --no-traffic
 cap ldpc_bp_minsum ldpc_bp_qc_kernel python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-links --no-variants --no-traffic --cn-update minsum
 cap frontend_mimo ofdm_frontend_kernel python bench.py --workload mimo_ofdm --steps 2 --no-cpu-baseline
 cap frontend_pusch ofdm_frontend_kernel python bench.py --workload pusch --steps 2 --no-cpu-baseline --batch 2048
-cap cir_apply cir_apply_kernel python tools/pusch_sim.py --max-batches 1 --ebno-dbs 0 --global-batch 2048
-cap lmmse_diag ofdm_lmmse_diag_kernel python tools/bench_phy_kernels.py --only ofdm_lmmse_4x16
-cap fft76 ofdm_fft_small_kernel python tools/bench_phy_kernels.py --only ofdm_demodulate_76
+SKIP=0 cap cir_apply cir_apply_kernel python tools/pusch_sim.py --max-batches 1 --ebno-dbs 0 --global-batch 2048
+SKIP=0 cap lmmse_diag ofdm_lmmse_diag_kernel python tools/bench_phy_kernels.py --only ofdm_lmmse_4x16
+SKIP=0 cap fft76 ofdm_fft_small_kernel python tools/bench_phy_kernels.py --only ofdm_demodulate_76
 ls -la gpurun_out/*.ncu-rep | wc -l
+# text summaries on the box (the .ncu-rep files come back too while they fit gpurun_out's 64 MiB)
+for f in gpurun_out/${R}_*.ncu-rep; do python tools/ncu_summary.py $f ${f%.ncu-rep}_ncu.txt > /dev/null 2>&1; done
+while [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; do rm -f "$(ls -S gpurun_out/*.ncu-rep | head -1)"; done
+du -sh gpurun_out
