@@ -304,6 +304,13 @@ __device__ __forceinline__ float2* fft_small_warp(float2* x, float2* y, const fl
     return x;
 }
 
+__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+
+// A warp works on batches of FPW consecutive (row, symbol) jobs. Three shared-memory buffers per warp rotate: while the
+// FFT stages ping-pong between two of them, cp.async fills the third with the next batch's samples (no registers, the
+// global-load latency hides behind the butterflies).
 template <int DEMOD, int FPW>
 __global__ void __launch_bounds__(256, 2) ofdm_fft_small_kernel(const float2* __restrict__ x, float2* __restrict__ out,
                                                              const __grid_constant__ SmallFftPlan plan, int nsym,
@@ -325,59 +332,82 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft_small_kernel(const float2* __
         }
     }
     __syncthreads();
-    float2* b0 = bufs + (size_t)2 * FPW * N * warp;
-    float2* b1 = b0 + (size_t)FPW * N;
+    float2* bin = bufs + (size_t)3 * FPW * N * warp;               // receives the next batch
+    float2* bx = bin + (size_t)FPW * N;
+    float2* by = bx + (size_t)FPW * N;
     const float scale = 1.0f / sqrtf((float)N);
     const long long jobs = rows * nsym;
     const int h = N / 2;
-    for (long long jb = ((long long)blockIdx.x * nwarps + warp) * FPW; jb < jobs; jb += (long long)gridDim.x * nwarps * FPW) {
+    const long long jstep = (long long)gridDim.x * nwarps * FPW;
+
+    // asynchronous copy of batch jb into dst: the demodulator copies the samples behind the cyclic prefix, the modulator
+    // applies the ifftshift to the source index (the conjugation of ifft = conj(fft(conj(.))) / N happens on arrival)
+    auto prefetch = [&](long long jb, float2* dst) {
+        if (jb < jobs) {
+            long long row = jb / nsym;
+            int l = (int)(jb - row * nsym);
 #pragma unroll
-        for (int f = 0; f < FPW; ++f) {
-            const long long job = jb + f;
-            if (job >= jobs) break;                                // tail: stale buffer contents are transformed, never stored
-            const int l = (int)(job % nsym);
-            float2* dstb = b0 + f * N;
-            if (DEMOD) {
-                const float2* src = x + (job / nsym) * len + off[l] + cp[l];
-                for (int k = lane; k < N; k += 32) dstb[k] = src[k];
-            } else {
-                const float2* src = x + job * N;
-                for (int k = lane; k < N; k += 32) {
-                    int ks = k;
-                    if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // ifftshift
-                    float2 v = src[ks];
-                    dstb[k] = make_float2(v.x, -v.y);              // ifft = conj(fft(conj(x))) / N
+            for (int f = 0; f < FPW; ++f) {
+                if (jb + f < jobs) {                               // tail: stale buffer contents are transformed, never stored
+                    if (DEMOD) {
+                        const float2* src = x + row * len + off[l] + cp[l];
+                        for (int k = lane; k < N; k += 32) cp_async8(dst + f * N + k, src + k);
+                    } else {
+                        const float2* src = x + (jb + f) * N;
+                        for (int k = lane; k < N; k += 32) {
+                            int ks = k;
+                            if (shift) { ks = k + h; ks -= ks >= N ? N : 0; }   // ifftshift
+                            cp_async8(dst + f * N + k, src + ks);
+                        }
+                    }
                 }
+                if (++l == nsym) { l = 0; ++row; }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    long long jb = ((long long)blockIdx.x * nwarps + warp) * FPW;
+    prefetch(jb, bin);
+    for (; jb < jobs; jb += jstep) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        const float2* res = fft_small_warp<FPW>(b0, b1, W, plan, lane);
+        { float2* t = bin; bin = bx; bx = t; }                     // bx: this batch; bin: free again (stored last round)
+        prefetch(jb + jstep, bin);
+        if (!DEMOD) {
+            for (int k = lane; k < FPW * N; k += 32) bx[k].y = -bx[k].y;
+            __syncwarp();
+        }
+        const float2* res = fft_small_warp<FPW>(bx, by, W, plan, lane);
+        long long row = jb / nsym;
+        int l = (int)(jb - row * nsym);
 #pragma unroll
         for (int f = 0; f < FPW; ++f) {
-            const long long job = jb + f;
-            if (job >= jobs) break;
-            const int l = (int)(job % nsym);
-            const float2* rf = res + f * N;
-            if (DEMOD) {
-                float2* dst = out + job * N;
-                for (int k = lane; k < N; k += 32) {
-                    int ks = k;
-                    if (shift) { ks = k + h; if (ks >= N) ks -= N; }   // fftshift
-                    dst[ks] = cmul(cscale(rf[k], scale), PC[k]);
-                }
-            } else {
-                const int c = cp[l];
-                float2* dst = out + (job / nsym) * len + off[l];
-                for (int i = lane; i < N + c; i += 32) {
-                    int k = i - c;
-                    if (k < 0) k += N;
-                    float2 v = rf[k];
-                    dst[i] = make_float2(v.x * scale, -v.y * scale);
+            if (jb + f < jobs) {
+                const float2* rf = res + f * N;
+                if (DEMOD) {
+                    float2* dst = out + (jb + f) * N;
+                    for (int k = lane; k < N; k += 32) {
+                        int ks = k;
+                        if (shift) { ks = k + h; ks -= ks >= N ? N : 0; }   // fftshift
+                        dst[ks] = cmul(cscale(rf[k], scale), PC[k]);
+                    }
+                } else {
+                    const int c = cp[l];
+                    float2* dst = out + row * len + off[l];
+                    for (int i = lane; i < N + c; i += 32) {
+                        int k = i - c;
+                        k += k < 0 ? N : 0;
+                        const float2 v = rf[k];
+                        dst[i] = make_float2(v.x * scale, -v.y * scale);
+                    }
                 }
             }
+            if (++l == nsym) { l = 0; ++row; }
         }
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -989,7 +1019,7 @@ template <int DEMOD, int FPW>
 int launch_fft_small_fpw(const SmallFftPlan& sp, const float2* x, float2* out, int nsym, const int* cp, const int* off,
                          int len, int l_min, long long rows, int shift, cudaStream_t stream) {
     const int warps = 8, n = sp.n;
-    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 2 * FPW * warps);
+    size_t smem = sizeof(float2) * (size_t)n * ((DEMOD ? 2 : 1) + 3 * FPW * warps);
     auto kern = ofdm_fft_small_kernel<DEMOD, FPW>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -1009,10 +1039,10 @@ int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* c
     if (rc) return rc;
     // transforms per warp (SB_FFT_FPW overrides, for experiments). Measured at N = 76: 1 -> 0.82 ms, 4 -> 0.55 ms,
     // 8 -> 0.63 ms per 458 k transforms (8 halves the resident warps per SM).
-    int fpw = n <= 128 ? 4 : (n <= 384 ? 2 : 1);
+    int fpw = n <= 128 ? 4 : (n <= 256 ? 2 : 1);               // three buffers of fpw transforms per warp, 2 CTAs per SM
     if (const char* e = getenv("SB_FFT_FPW")) {
         int v = atoi(e);
-        if ((v == 1 || v == 2 || v == 4 || v == 8) && (size_t)n * 8 * (2 + 16 * v) <= 160 * 1024) fpw = v;
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && (size_t)n * 8 * (2 + 24 * v) <= 200 * 1024) fpw = v;
     }
     if (fpw == 8) return launch_fft_small_fpw<DEMOD, 8>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);
     if (fpw == 4) return launch_fft_small_fpw<DEMOD, 4>(sp, x, out, nsym, cp, off, len, l_min, rows, shift, stream);

@@ -26,3 +26,13 @@ def cuda_device(sb_lib):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(autouse=True)
+def _seed_per_test(request):
+    """Every test starts from its own fixed seed (CRC of the test id), so random inputs do not depend on which tests ran
+    before it; tests that need a particular stream still set ``config.seed`` themselves."""
+    import zlib
+    from sionna_b200.phy import config
+    config.seed = zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF
+    yield
