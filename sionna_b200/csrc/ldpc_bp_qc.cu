@@ -76,9 +76,12 @@ struct QcParams {
 #define SB_PHI_LO 8.5e-8f
 // SC = false: plain evaluation; one vote per check on its first edge pair probes for saturation and raises *sat_flag,
 // which makes the CTA use the SC = true variant (votes on every pair) from the next iteration on.
+// Out of line on purpose: the five degree classes then share ONE copy of each variant's loops (the kernel is bound by
+// instruction fetch as much as by issue: 12.35 -> 11.85 ms per 4096 codewords at 2 dB; making phi itself a call costs more
+// than it saves, 12.8 ms).
 template <bool SC, class LT>
-__device__ __forceinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
-                                          const LT& lt) {
+__device__ __noinline__ void cn_phi_qc(float* pm, int Z, int deg, float clip, float phi_max, int* sat_flag,
+                                       const LT& lt) {
     const unsigned am = __activemask();                   // lanes of this warp working on the same block row
     float P = 0.f;
     unsigned par = 0;
