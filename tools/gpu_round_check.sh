@@ -11,6 +11,7 @@ for w in qpsk_awgn ofdm_siso mimo_ofdm pusch; do
   python bench.py --workload $w --steps 10 > gpurun_out/${R}_bench_$w.json 2> gpurun_out/bench_$w.err
 done
 python tools/bench_phy_kernels.py --out gpurun_out/${R}_phy_kernels.json 2>&1 | tail -14
+python tools/pusch_sim.py --out gpurun_out/${R}_pusch_1gpu.json 2>&1 | tail -1 | cut -c1-300
 # launch lists (shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_phi.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-links --no-variants --no-traffic > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 500 --csv --log-file gpurun_out/${R}_launches_pusch.csv python tools/pusch_sim.py --max-batches 2 --ebno-dbs 0,2 > /dev/null 2>&1
