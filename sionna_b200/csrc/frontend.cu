@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kTile) ofdm_frontend_kernel(const __grid_const
                 yp[c] = yb + (long long)m * p.GRID;
                 const float nn = nb[m * p.no_stride[2]];
                 // whitening by 1 / sqrt(no + sum_q err_var_q), err_var_q = no * E_q  (ofdm/equalization.py:205-218)
-                w[c] = (m0 + c < p.ANT) ? 1.0f / sqrtf(nn + nn * es) : 0.f;
+                w[c] = (m0 + c < p.ANT) ? rsqrtf(nn + nn * es) : 0.f;       // MUFU.RSQ, <= 2 ulp
 #pragma unroll
                 for (int k = 0; k < K; ++k) h[c][k] = make_float2(0.f, 0.f);
             }

@@ -912,40 +912,61 @@ __global__ void __launch_bounds__(128, 4) ofdm_lmmse_diag_kernel(const OfdmEqPar
         for (int k = 0; k < K; ++k) z[k] = make_float2(0.f, 0.f);
         // antennas in chunks of 4: all loads of a chunk (y, K channel columns, the error variances, no) are issued before
         // any of them is used, so 4 * (K + 1) 8-byte loads per thread are in flight instead of one dependent load at a
-        // time (the one-antenna-per-trip version was latency bound: long_scoreboard 3.4 warps per issue, 27 % of HBM peak)
+        // time (the one-antenna-per-trip version was latency bound: long_scoreboard 3.4 warps per issue, 27 % of HBM peak).
+        // Running pointers (one 64-bit add per array and antenna) instead of a 64-bit product per load.
         constexpr int CH = 4;
         const long long row0 = (b * p.RX + rx) * M;
+        const float2* yp = p.y + row0 * SF + re;                                    // antenna stride SF
+        const float2* hp[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) hp[k] = p.hhat + (row0 * p.TXS + des[k]) * SF + re;   // antenna stride TXS * SF
+        const long long hstep = (long long)p.TXS * SF;
         const float* evp = p.ev + b * p.ev_stride[0] + rx * p.ev_stride[1] + s * p.ev_stride[4] + f * p.ev_stride[5];
         const float* nop = p.no + b * p.no_stride[0] + rx * p.no_stride[1];
-        for (int m0 = 0; m0 < M; m0 += CH) {
+        const long long ev_m = p.ev_stride[2], ev_q = p.ev_stride[3], no_m = p.no_stride[2];
+        auto accumulate = [&](float2 yv, const float2* hv, float d) {
+            // whitening by 1 / sqrt(d): one division per antenna, multiplications for the K + 1 scalings
+            const float w = rsqrtf(d);                                    // MUFU.RSQ, <= 2 ulp
+            const float2 yw = make_float2(yv.x * w, yv.y * w);
+            float2 hw[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) hw[k] = make_float2(hv[k].x * w, hv[k].y * w);
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                z[a] = cadd(z[a], cmulc(yw, hw[a]));                       // conj(H_w[m, a]) * y_w[m]
+#pragma unroll
+                for (int q = 0; q <= a; ++q) Bm[a * (a + 1) / 2 + q] = cadd(Bm[a * (a + 1) / 2 + q], cmulc(hw[q], hw[a]));
+            }
+        };
+        int m0 = 0;
+#pragma unroll 1
+        for (; m0 + CH <= M; m0 += CH) {
             float2 yv[CH], hv[CH][K];
             float dv[CH];
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const int m = min(m0 + c, M - 1);
-                const long long row = row0 + m;
-                yv[c] = p.y[row * SF + re];
+                yv[c] = yp[c * SF];
 #pragma unroll
-                for (int k = 0; k < K; ++k) hv[c][k] = p.hhat[(row * p.TXS + des[k]) * SF + re];
+                for (int k = 0; k < K; ++k) hv[c][k] = hp[k][c * hstep];
                 float evs = 0.f;
-                for (int q = 0; q < p.TXS; ++q) evs += evp[m * p.ev_stride[2] + q * p.ev_stride[3]];
-                dv[c] = nop[m * p.no_stride[2]] + evs;
+                for (int q = 0; q < p.TXS; ++q) evs += evp[(m0 + c) * ev_m + q * ev_q];
+                dv[c] = nop[(m0 + c) * no_m] + evs;
             }
+            yp += CH * SF;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                // whitening by 1 / sqrt(d): one division per antenna, multiplications for the K + 1 scalings
-                const float w = (m0 + c < M) ? 1.0f / sqrtf(dv[c]) : 0.f;
-                const float2 yw = make_float2(yv[c].x * w, yv[c].y * w);
-                float2 hw[K];
+            for (int k = 0; k < K; ++k) hp[k] += CH * hstep;
 #pragma unroll
-                for (int k = 0; k < K; ++k) hw[k] = make_float2(hv[c][k].x * w, hv[c][k].y * w);
+            for (int c = 0; c < CH; ++c) accumulate(yv[c], hv[c], dv[c]);
+        }
+#pragma unroll 1
+        for (; m0 < M; ++m0) {                                                      // M not a multiple of 4
+            float2 hv[K];
 #pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    z[a] = cadd(z[a], cmulc(yw, hw[a]));               // conj(H_w[m, a]) * y_w[m]
-#pragma unroll
-                    for (int q = 0; q <= a; ++q) Bm[a * (a + 1) / 2 + q] = cadd(Bm[a * (a + 1) / 2 + q], cmulc(hw[q], hw[a]));
-                }
-            }
+            for (int k = 0; k < K; ++k) { hv[k] = *hp[k]; hp[k] += hstep; }
+            float evs = 0.f;
+            for (int q = 0; q < p.TXS; ++q) evs += evp[m0 * ev_m + q * ev_q];
+            accumulate(*yp, hv, nop[m0 * no_m] + evs);
+            yp += SF;
         }
         float2 xo[K];
         float no_e[K];

@@ -54,6 +54,30 @@ def test_mapper_exact(cuda_device, m):
     assert np.array_equal(x.cpu().numpy(), M.mapper(bits[..., :12], M.pam(3))[0])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m", [4, 6, 8, 10])
+def test_demapper_app_high_snr_group_underflow(cuda_device, m):
+    """`app` demapping when whole bit groups underflow relative to the dimension's largest exponent (|LLR| > 85, noise
+    variance down to 1e-4): the kernel's out-of-line per-group path, including its shortcut that returns the group maximum
+    without evaluating exp when every other member is below e^-21 of it, equals the oracle's per-group logsumexp bit for
+    bit (kernel math) and the libm oracle to 1e-4."""
+    from sionna_b200.phy.mapping import Demapper
+    rng = np.random.default_rng(70 + m)
+    pts = M.qam(m)
+    x, _ = M.mapper(rng.integers(0, 2, (4, 7, 24 * m)), pts)
+    dem = Demapper("app", "qam", m)
+    for no in (2e-2, 2e-3, 1e-4):
+        y = (x + (rng.normal(size=x.shape) + 1j * rng.normal(size=x.shape)) * np.sqrt(no / 2)).astype(np.complex64)
+        llr = dem(torch.from_numpy(y).to(cuda_device), no).cpu().numpy()
+        assert np.isfinite(llr).all() and np.abs(llr).max() > 85
+        assert np.array_equal(llr, M.demapper(y, np.float32(no), pts, "app", math_mode=1))
+        np.testing.assert_allclose(llr, M.demapper(y, np.float32(no), pts, "app", math_mode=0), rtol=1e-4, atol=2e-5)
+    no_sym = (10.0 ** rng.uniform(-4, -1, size=y.shape)).astype(np.float32)
+    out = dem(torch.from_numpy(y).to(cuda_device), torch.from_numpy(no_sym).to(cuda_device)).cpu().numpy()
+    assert np.array_equal(out, M.demapper(y, no_sym, pts, "app", math_mode=1))
+
+
+
 @pytest.mark.parametrize("method", ["app", "maxlog"])
 @pytest.mark.parametrize("m", [2, 4, 6, 8, 10])
 def test_demapper_vs_oracle(cuda_device, m, method):
