@@ -411,6 +411,181 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft_small_kernel(const float2* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// N = 4096 (the 100 MHz NR grid): three in-place radix-16 passes (decimation in frequency) instead of six radix-4
+// Stockham passes. A thread owns one radix-16 butterfly per pass (16 points in registers, two levels of radix-4 with
+// the constant 16th roots between them), so a pass is one shared-memory round trip and 256 threads cover the transform.
+// In place means ONE data buffer per transform: a second one receives the next transform by cp.async while this one is
+// computed, and two CTAs fit on an SM. The result sits in hex-digit-reversed order (X[j0 + 16 j1 + 256 j2] at position
+// 256 j0 + 16 j1 + j2); the copy-out loop undoes that. The buffer is padded (i + i/16 + i/256) so that all three pass
+// patterns and the digit-reversed copy-out are bank-conflict free. The demodulator's phase-compensation factors of the
+// 16 bins a thread copies out live in registers for the lifetime of the (persistent) CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBigN = 4096;
+constexpr int kBigPad = kBigN + kBigN / 16 + kBigN / 256;
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4) + (i >> 8); }
+
+__device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {   // b_c = sum_r a_r (-j)^(r c)
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    const float2 d13j = make_float2(d13.y, -d13.x);                   // -j (a1 - a3)
+    a0 = cadd(s02, s13);
+    a1 = cadd(d02, d13j);
+    a2 = csub(s02, s13);
+    a3 = csub(d02, d13j);
+}
+
+// u[j'] = sum_j v[j] W16^(j j') in place; on return v[j1' + 4 j0'] holds output j' = j1' + 4 j0'
+__device__ __forceinline__ void radix16(float2* v) {
+    // level 1: radix-4 over j1 for each j0 (elements j0 + 4 j1), then the 16th roots W16^(j0 j1')
+#pragma unroll
+    for (int j0 = 0; j0 < 4; ++j0) radix4(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);   // v[j0 + 4 j1'] = a[j0][j1']
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    // W16^q = (cos(2 pi q / 16), -sin(2 pi q / 16)), q = j0 * j1'
+    v[5] = cmul(v[5], make_float2(c1, -s1));          // j0 = 1, j1' = 1: q = 1
+    v[9] = cmul(v[9], make_float2(h, -h));            // j0 = 1, j1' = 2: q = 2
+    v[13] = cmul(v[13], make_float2(s1, -c1));        // j0 = 1, j1' = 3: q = 3
+    v[6] = cmul(v[6], make_float2(h, -h));            // j0 = 2, j1' = 1: q = 2
+    v[10] = make_float2(v[10].y, -v[10].x);           // j0 = 2, j1' = 2: q = 4: -j
+    v[14] = cmul(v[14], make_float2(-h, -h));         // j0 = 2, j1' = 3: q = 6
+    v[7] = cmul(v[7], make_float2(s1, -c1));          // j0 = 3, j1' = 1: q = 3
+    v[11] = cmul(v[11], make_float2(-h, -h));         // j0 = 3, j1' = 2: q = 6
+    v[15] = cmul(v[15], make_float2(-c1, s1));        // j0 = 3, j1' = 3: q = 9
+    // level 2: radix-4 over j0 for each j1' (elements 4 j1' + j0): output j0' lands at v[4 j1' + j0'] = u[j1' + 4 j0']
+#pragma unroll
+    for (int j1 = 0; j1 < 4; ++j1) radix4(v[4 * j1], v[4 * j1 + 1], v[4 * j1 + 2], v[4 * j1 + 3]);
+}
+
+template <int DEMOD>
+__global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __restrict__ x, float2* __restrict__ out, int nsym,
+                                                           const int* __restrict__ cp, const int* __restrict__ off,
+                                                           int len, int l_min, long long rows, int shift) {
+    constexpr int N = kBigN;
+    extern __shared__ float2 sm[];
+    float2* W = sm;                                                  // exp(-2 pi i k / N)
+    float2* buf0 = sm + N;
+    float2* buf1 = buf0 + kBigPad;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < N; k += 256) {
+        float sn, cs;
+        sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
+        W[k] = make_float2(cs, sn);
+    }
+    float2 pc[16];                                                   // demodulator: phase compensation of bins tid + 256 i
+    if (DEMOD) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            // tmp = -2 pi l_min / N * k in fp32 as the reference computes it, then exp(j tmp)
+            const float tmp = -2.0f * 3.14159265358979323846f * (float)l_min / (float)N * (float)(tid + 256 * i);
+            pc[i] = make_float2(cosf(tmp), sinf(tmp));
+        }
+    }
+    const float scale = 1.0f / 64.0f;                                // 1 / sqrt(4096)
+    const long long jobs = rows * nsym;
+    auto prefetch = [&](long long job, float2* dst) {
+        if (job < jobs) {
+            if (DEMOD) {
+                const long long row = job / nsym;
+                const int l = (int)(job - row * nsym);
+                const float2* src = x + row * len + off[l] + cp[l];
+                for (int k = tid; k < N; k += 256) cp_async8(dst + pad16(k), src + k);
+            } else {
+                const float2* src = x + job * N;
+                for (int k = tid; k < N; k += 256) cp_async8(dst + pad16(k), src + (shift ? ((k + N / 2) & (N - 1)) : k));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float2* cur = buf0;
+    float2* nxt = buf1;
+    long long job = blockIdx.x;
+    prefetch(job, cur);
+    for (; job < jobs; job += gridDim.x) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                             // data of `job` visible; `nxt` no longer read by anyone
+        prefetch(job + gridDim.x, nxt);
+        float2 v[16];
+        // pass 0: n = m + 256 j, m = tid; twiddle W_N^(m j')
+        {
+            const int m = tid;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = cur[pad16(m + 256 * j)];
+                if (!DEMOD) v[j].y = -v[j].y;                        // ifft = conj(fft(conj(.))) / N
+            }
+            radix16(v);
+#pragma unroll
+            for (int jp = 0; jp < 16; ++jp) {                        // output j' = j1' + 4 j0' is v[4 j1' + j0']
+                const int e = 4 * (jp & 3) + (jp >> 2);
+                float2 u = v[e];
+                if (jp) u = cmul(u, W[m * jp]);
+                cur[pad16(m + 256 * jp)] = u;
+            }
+        }
+        __syncthreads();
+        // pass 1: inside block b (256 points): m' + 16 j; twiddle W_256^(m' j') = W_N^(16 m' j')
+        {
+            const int b = tid >> 4, mp = tid & 15, base = 256 * b + mp;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = cur[pad16(base + 16 * j)];
+            radix16(v);
+#pragma unroll
+            for (int jp = 0; jp < 16; ++jp) {
+                const int e = 4 * (jp & 3) + (jp >> 2);
+                float2 u = v[e];
+                if (jp) u = cmul(u, W[16 * mp * jp]);
+                cur[pad16(base + 16 * jp)] = u;
+            }
+        }
+        __syncthreads();
+        // pass 2: 16 contiguous points, no twiddle
+        {
+            const int base = 16 * tid;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = cur[pad16(base + j)];
+            radix16(v);
+#pragma unroll
+            for (int jp = 0; jp < 16; ++jp) cur[pad16(base + jp)] = v[4 * (jp & 3) + (jp >> 2)];
+        }
+        __syncthreads();
+        // copy-out: X[k], k = j0 + 16 j1 + 256 j2, sits at 256 j0 + 16 j1 + j2
+        const long long row = job / nsym;
+        const int l = (int)(job - row * nsym);
+        if (DEMOD) {
+            float2* dst = out + job * N;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = tid + 256 * i;
+                const int pos = ((k & 15) << 8) | (k & 0xf0) | (k >> 8);
+                const int ks = shift ? ((k + N / 2) & (N - 1)) : k;  // fftshift
+                dst[ks] = cmul(cscale(cur[pad16(pos)], scale), pc[i]);
+            }
+        } else {
+            const int c = cp[l];
+            float2* dst = out + row * len + off[l];
+            for (int i = tid; i < N + c; i += 256) {
+                const int k = (i - c) & (N - 1);
+                const int pos = ((k & 15) << 8) | (k & 0xf0) | (k >> 8);
+                const float2 v0 = cur[pad16(pos)];
+                dst[i] = make_float2(v0.x * scale, -v0.y * scale);
+            }
+        }
+        { float2* t = cur; cur = nxt; nxt = t; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int DEMOD>
+int launch_fft4096(const float2* x, float2* out, int nsym, const int* cp, const int* off, int len, int l_min, long long rows,
+                   int shift, cudaStream_t stream) {
+    const size_t smem = sizeof(float2) * ((size_t)kBigN + 2 * kBigPad);
+    auto kern = ofdm_fft4096_kernel<DEMOD>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long jobs = rows * nsym;
+    const int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 2);
+    kern<<<grid, 256, smem, stream>>>(x, out, nsym, cp, off, len, l_min, rows, shift);
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // out[b, r, j] = in[b, (in_rows == 1 ? 0 : r), idx[r, j]]  (idx < 0 -> 0).  WORDS = 32-bit words per element: 1 (float),
 // 2 (complex64 / float64) or 4 (complex128) -- a bit copy, so the wider types need no arithmetic variant.
 template <int WORDS>
@@ -1086,6 +1261,13 @@ extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, in
         SB_LAUNCH_CHECK();
         return SB_OK;
     }
+    if (fft_size == kBigN) {
+        int rc = launch_fft4096<0>((const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_out_off, out_len, 0, rows, shift,
+                                   (cudaStream_t)stream);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        return SB_OK;
+    }
     FftPlan plan;
     SB_CHECK_ARG(make_plan(fft_size, &plan) == 0, "sb_ofdm_modulate: fft_size has too many factors");
     int threads = std::min(256, std::max(32, (fft_size / 2 + 31) / 32 * 32));
@@ -1118,6 +1300,13 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
     if (fft_size <= kSmallFftMax) {
         int rc = launch_fft_small<1>((const float2*)d_x, (float2*)d_out, fft_size, num_symbols, d_cp, d_in_off, in_len,
                                      l_min, rows, shift, (cudaStream_t)stream);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        return SB_OK;
+    }
+    if (fft_size == kBigN) {
+        int rc = launch_fft4096<1>((const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_in_off, in_len, l_min, rows, shift,
+                                   (cudaStream_t)stream);
         if (rc) return rc;
         SB_LAUNCH_CHECK();
         return SB_OK;

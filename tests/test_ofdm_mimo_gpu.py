@@ -39,6 +39,24 @@ def test_ofdm_mod_demod_vs_oracle(cuda_device, n):
     assert OFDMDemodulator(n, 0, 5)(pad).shape == x.shape                   # trailing samples dropped
 
 
+def test_ofdm_4096_many_symbols_per_cta(cuda_device):
+    """4096-point grid with more OFDM symbols than resident CTAs: every CTA of the radix-16 kernel transforms several
+    symbols, so its cp.async prefetch of the next symbol into the second buffer is exercised (the per-size test above has
+    fewer symbols than CTAs). Oracle on the first and last frame, round trip on all."""
+    from sionna_b200.phy.ofdm import OFDMModulator, OFDMDemodulator
+    rng = np.random.default_rng(4096)
+    n, cp = 4096, 288
+    x = _c64(rng, (48, 14, n))
+    t = OFDMModulator(cp)(torch.from_numpy(x).to(cuda_device))
+    for r in (0, 47):
+        np.testing.assert_allclose(t[r].cpu().numpy(), F.ofdm_modulate(x[r].astype(np.complex128), cp), atol=2e-4, rtol=1e-4)
+    xh = OFDMDemodulator(n, -6, cp)(t)
+    for r in (0, 47):
+        np.testing.assert_allclose(xh[r].cpu().numpy(), F.ofdm_demodulate(F.ofdm_modulate(x[r].astype(np.complex128), cp), n, -6, cp),
+                                   atol=3e-4, rtol=1e-4)
+    assert np.abs(OFDMDemodulator(n, 0, cp)(t).cpu().numpy() - x).max() < 2e-4
+
+
 def _grid(num_tx, num_streams, num_sym=14, fft=76, pilots=(2, 11)):
     from sionna_b200.phy.ofdm import ResourceGrid
     return ResourceGrid(num_sym, fft, 15e3, num_tx=num_tx, num_streams_per_tx=num_streams, cyclic_prefix_length=6,
