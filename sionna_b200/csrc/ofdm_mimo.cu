@@ -22,9 +22,6 @@
 #include <cstdlib>
 #include <vector>
 #include "sb_common.h"
-#include <map>
-#include <mutex>
-#include <vector>
 #include "rng.cuh"
 #include "lmmse_diag.cuh"
 
@@ -1233,8 +1230,8 @@ int launch_fft_small(const float2* x, float2* out, int n, int nsym, const int* c
     SmallFftPlan sp;
     int rc = get_small_plan(n, &sp);
     if (rc) return rc;
-    // transforms per warp (SB_FFT_FPW overrides, for experiments). Measured at N = 76: 1 -> 0.82 ms, 4 -> 0.55 ms,
-    // 8 -> 0.63 ms per 458 k transforms (8 halves the resident warps per SM).
+    // transforms per warp (SB_FFT_FPW overrides, for experiments). Measured at N = 76, modulator / demodulator ms per
+    // 458 k transforms: 2 -> 0.39 / 0.37, 4 -> 0.277 / 0.254, 8 -> 0.34 / 0.29 (8 halves the resident warps per SM).
     int fpw = n <= 128 ? 4 : (n <= 256 ? 2 : 1);               // three buffers of fpw transforms per warp, 2 CTAs per SM
     if (const char* e = getenv("SB_FFT_FPW")) {
         int v = atoi(e);
