@@ -457,14 +457,18 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
                                                            int len, int l_min, long long rows, int shift) {
     constexpr int N = kBigN;
     extern __shared__ float2 sm[];
-    float2* W = sm;                                                  // exp(-2 pi i k / N)
-    float2* buf0 = sm + N;
+    // twiddles laid out the way the passes read them (lanes along the fastest index: conflict-free):
+    //   T0[j' * 256 + m] = W_N^(m j') for pass 0,  T1[j' * 16 + m'] = W_256^(m' j') for pass 1
+    float2* T0 = sm;
+    float2* T1 = sm + N;
+    float2* buf0 = T1 + 256;
     float2* buf1 = buf0 + kBigPad;
     const int tid = threadIdx.x;
-    for (int k = tid; k < N; k += 256) {
+    for (int e = tid; e < N + 256; e += 256) {
+        const int k = e < N ? (e & 255) * (e >> 8) : 16 * ((e - N) & 15) * ((e - N) >> 4);   // exponent of W_N, < N
         float sn, cs;
         sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
-        W[k] = make_float2(cs, sn);
+        sm[e] = make_float2(cs, sn);
     }
     float2 pc[16];                                                   // demodulator: phase compensation of bins tid + 256 i
     if (DEMOD) {
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
             for (int jp = 0; jp < 16; ++jp) {                        // output j' = j1' + 4 j0' is v[4 j1' + j0']
                 const int e = 4 * (jp & 3) + (jp >> 2);
                 float2 u = v[e];
-                if (jp) u = cmul(u, W[m * jp]);
+                if (jp) u = cmul(u, T0[jp * 256 + m]);
                 cur[pad16(m + 256 * jp)] = u;
             }
         }
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
             for (int jp = 0; jp < 16; ++jp) {
                 const int e = 4 * (jp & 3) + (jp >> 2);
                 float2 u = v[e];
-                if (jp) u = cmul(u, W[16 * mp * jp]);
+                if (jp) u = cmul(u, T1[jp * 16 + mp]);
                 cur[pad16(base + 16 * jp)] = u;
             }
         }
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
 template <int DEMOD>
 int launch_fft4096(const float2* x, float2* out, int nsym, const int* cp, const int* off, int len, int l_min, long long rows,
                    int shift, cudaStream_t stream) {
-    const size_t smem = sizeof(float2) * ((size_t)kBigN + 2 * kBigPad);
+    const size_t smem = sizeof(float2) * ((size_t)kBigN + 256 + 2 * kBigPad);
     auto kern = ofdm_fft4096_kernel<DEMOD>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long jobs = rows * nsym;
