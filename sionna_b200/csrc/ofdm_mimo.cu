@@ -408,17 +408,16 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft_small_kernel(const float2* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// N = 4096 (the 100 MHz NR grid): three in-place radix-16 passes (decimation in frequency) instead of six radix-4
-// Stockham passes. A thread owns one radix-16 butterfly per pass (16 points in registers, two levels of radix-4 with
-// the constant 16th roots between them), so a pass is one shared-memory round trip and 256 threads cover the transform.
-// In place means ONE data buffer per transform: a second one receives the next transform by cp.async while this one is
-// computed, and two CTAs fit on an SM. The result sits in hex-digit-reversed order (X[j0 + 16 j1 + 256 j2] at position
-// 256 j0 + 16 j1 + j2); the copy-out loop undoes that. The buffer is padded (i + i/16 + i/256) so that all three pass
-// patterns and the digit-reversed copy-out are bank-conflict free. The demodulator's phase-compensation factors of the
-// 16 bins a thread copies out live in registers for the lifetime of the (persistent) CTA.
+// N = 4096 and 2048 (the 100 / 50 MHz NR grids), N = R0 * 256 with R0 = 16 / 8: three in-place passes (decimation in
+// frequency) - radix R0, radix 16, radix 16 - instead of six radix-4 Stockham passes. A thread owns one butterfly per
+// pass (up to 16 points in registers, two levels of radix-4 / radix-2 with the constant roots between them), so a pass is
+// one shared-memory round trip and 256 threads cover the transform. In place means ONE data buffer per transform: a
+// second one receives the next transform by cp.async while this one is computed, and two CTAs fit on an SM. The result
+// sits in digit-reversed order (X[j0 + R0 (j1 + 16 j2)] at position 256 j0 + 16 j1 + j2); the copy-out loop undoes that.
+// The buffer is padded (i + i/16 + i/256) so that the pass patterns and the digit-reversed copy-out are (nearly) bank-
+// conflict free, and the inter-pass twiddles are stored the way the passes read them. The demodulator's phase-
+// compensation factors of the R0 bins a thread copies out live in registers for the lifetime of the (persistent) CTA.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBigN = 4096;
-constexpr int kBigPad = kBigN + kBigN / 16 + kBigN / 256;
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4) + (i >> 8); }
 
 __device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {   // b_c = sum_r a_r (-j)^(r c)
@@ -430,7 +429,7 @@ __device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float
     a3 = csub(d02, d13j);
 }
 
-// u[j'] = sum_j v[j] W16^(j j') in place; on return v[j1' + 4 j0'] holds output j' = j1' + 4 j0'
+// 16-point DFT in place; on return output j' = j1' + 4 j0' is v[4 j1' + j0']
 __device__ __forceinline__ void radix16(float2* v) {
     // level 1: radix-4 over j1 for each j0 (elements j0 + 4 j1), then the 16th roots W16^(j0 j1')
 #pragma unroll
@@ -451,35 +450,56 @@ __device__ __forceinline__ void radix16(float2* v) {
     for (int j1 = 0; j1 < 4; ++j1) radix4(v[4 * j1], v[4 * j1 + 1], v[4 * j1 + 2], v[4 * j1 + 3]);
 }
 
-template <int DEMOD>
-__global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __restrict__ x, float2* __restrict__ out, int nsym,
+// 8-point DFT in place (j = j0 + 2 j1: radix-4 over j1, the 8th roots, radix-2 over j0); on return output
+// j' = j1' + 4 j0' is v[2 j1' + j0']
+__device__ __forceinline__ void radix8(float2* v) {
+    radix4(v[0], v[2], v[4], v[6]);                   // a[0][j1'] at v[2 j1']
+    radix4(v[1], v[3], v[5], v[7]);                   // a[1][j1'] at v[1 + 2 j1']
+    const float h = 0.70710678118654752f;
+    v[3] = cmul(v[3], make_float2(h, -h));            // W8^1
+    v[5] = make_float2(v[5].y, -v[5].x);              // W8^2 = -j
+    v[7] = cmul(v[7], make_float2(-h, -h));           // W8^3
+#pragma unroll
+    for (int j1 = 0; j1 < 4; ++j1) {
+        const float2 s = cadd(v[2 * j1], v[2 * j1 + 1]), d = csub(v[2 * j1], v[2 * j1 + 1]);
+        v[2 * j1] = s;
+        v[2 * j1 + 1] = d;
+    }
+}
+
+// register index of output j' of the first pass
+template <int R0>
+__device__ __forceinline__ constexpr int first_pass_slot(int jp) { return R0 == 16 ? 4 * (jp & 3) + (jp >> 2) : 2 * (jp & 3) + (jp >> 2); }
+
+template <int DEMOD, int R0>
+__global__ void __launch_bounds__(256, 2) ofdm_fft_r16_kernel(const float2* __restrict__ x, float2* __restrict__ out, int nsym,
                                                            const int* __restrict__ cp, const int* __restrict__ off,
                                                            int len, int l_min, long long rows, int shift) {
-    constexpr int N = kBigN;
+    constexpr int N = 256 * R0, PAD = N + N / 16 + N / 256, LOG_R0 = R0 == 16 ? 4 : 3;
     extern __shared__ float2 sm[];
     // twiddles laid out the way the passes read them (lanes along the fastest index: conflict-free):
     //   T0[j' * 256 + m] = W_N^(m j') for pass 0,  T1[j' * 16 + m'] = W_256^(m' j') for pass 1
     float2* T0 = sm;
     float2* T1 = sm + N;
     float2* buf0 = T1 + 256;
-    float2* buf1 = buf0 + kBigPad;
+    float2* buf1 = buf0 + PAD;
     const int tid = threadIdx.x;
     for (int e = tid; e < N + 256; e += 256) {
-        const int k = e < N ? (e & 255) * (e >> 8) : 16 * ((e - N) & 15) * ((e - N) >> 4);   // exponent of W_N, < N
+        const int k = e < N ? (e & 255) * (e >> 8) : R0 * ((e - N) & 15) * ((e - N) >> 4);   // exponent of W_N, < N
         float sn, cs;
         sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
         sm[e] = make_float2(cs, sn);
     }
-    float2 pc[16];                                                   // demodulator: phase compensation of bins tid + 256 i
+    float2 pc[R0];                                                   // demodulator: phase compensation of bins tid + 256 i
     if (DEMOD) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < R0; ++i) {
             // tmp = -2 pi l_min / N * k in fp32 as the reference computes it, then exp(j tmp)
             const float tmp = -2.0f * 3.14159265358979323846f * (float)l_min / (float)N * (float)(tid + 256 * i);
             pc[i] = make_float2(cosf(tmp), sinf(tmp));
         }
     }
-    const float scale = 1.0f / 64.0f;                                // 1 / sqrt(4096)
+    const float scale = 1.0f / sqrtf((float)N);
     const long long jobs = rows * nsym;
     auto prefetch = [&](long long job, float2* dst) {
         if (job < jobs) {
@@ -495,6 +515,8 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // position of bin k = j0 + R0 (j1 + 16 j2) in the buffer
+    auto bin_pos = [](int k) { return ((k & (R0 - 1)) << 8) | (((k >> LOG_R0) & 15) << 4) | (k >> (LOG_R0 + 4)); };
     float2* cur = buf0;
     float2* nxt = buf1;
     long long job = blockIdx.x;
@@ -504,41 +526,39 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
         __syncthreads();                                             // data of `job` visible; `nxt` no longer read by anyone
         prefetch(job + gridDim.x, nxt);
         float2 v[16];
-        // pass 0: n = m + 256 j, m = tid; twiddle W_N^(m j')
+        // pass 0 (radix R0): n = m + 256 j, m = tid; twiddle W_N^(m j')
         {
             const int m = tid;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < R0; ++j) {
                 v[j] = cur[pad16(m + 256 * j)];
                 if (!DEMOD) v[j].y = -v[j].y;                        // ifft = conj(fft(conj(.))) / N
             }
-            radix16(v);
+            if (R0 == 16) radix16(v); else radix8(v);
 #pragma unroll
-            for (int jp = 0; jp < 16; ++jp) {                        // output j' = j1' + 4 j0' is v[4 j1' + j0']
-                const int e = 4 * (jp & 3) + (jp >> 2);
-                float2 u = v[e];
+            for (int jp = 0; jp < R0; ++jp) {
+                float2 u = v[first_pass_slot<R0>(jp)];
                 if (jp) u = cmul(u, T0[jp * 256 + m]);
                 cur[pad16(m + 256 * jp)] = u;
             }
         }
         __syncthreads();
-        // pass 1: inside block b (256 points): m' + 16 j; twiddle W_256^(m' j') = W_N^(16 m' j')
-        {
+        // pass 1 (radix 16) inside block b of 256 points: m' + 16 j; twiddle W_256^(m' j'); 16 R0 butterflies
+        if (tid < 16 * R0) {
             const int b = tid >> 4, mp = tid & 15, base = 256 * b + mp;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = cur[pad16(base + 16 * j)];
             radix16(v);
 #pragma unroll
             for (int jp = 0; jp < 16; ++jp) {
-                const int e = 4 * (jp & 3) + (jp >> 2);
-                float2 u = v[e];
+                float2 u = v[4 * (jp & 3) + (jp >> 2)];
                 if (jp) u = cmul(u, T1[jp * 16 + mp]);
                 cur[pad16(base + 16 * jp)] = u;
             }
         }
         __syncthreads();
-        // pass 2: 16 contiguous points, no twiddle
-        {
+        // pass 2 (radix 16): 16 contiguous points, no twiddle
+        if (tid < 16 * R0) {
             const int base = 16 * tid;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = cur[pad16(base + j)];
@@ -547,25 +567,23 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
             for (int jp = 0; jp < 16; ++jp) cur[pad16(base + jp)] = v[4 * (jp & 3) + (jp >> 2)];
         }
         __syncthreads();
-        // copy-out: X[k], k = j0 + 16 j1 + 256 j2, sits at 256 j0 + 16 j1 + j2
+        // copy-out in natural bin order
         const long long row = job / nsym;
         const int l = (int)(job - row * nsym);
         if (DEMOD) {
             float2* dst = out + job * N;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < R0; ++i) {
                 const int k = tid + 256 * i;
-                const int pos = ((k & 15) << 8) | (k & 0xf0) | (k >> 8);
                 const int ks = shift ? ((k + N / 2) & (N - 1)) : k;  // fftshift
-                dst[ks] = cmul(cscale(cur[pad16(pos)], scale), pc[i]);
+                dst[ks] = cmul(cscale(cur[pad16(bin_pos(k))], scale), pc[i]);
             }
         } else {
             const int c = cp[l];
             float2* dst = out + row * len + off[l];
             for (int i = tid; i < N + c; i += 256) {
                 const int k = (i - c) & (N - 1);
-                const int pos = ((k & 15) << 8) | (k & 0xf0) | (k >> 8);
-                const float2 v0 = cur[pad16(pos)];
+                const float2 v0 = cur[pad16(bin_pos(k))];
                 dst[i] = make_float2(v0.x * scale, -v0.y * scale);
             }
         }
@@ -574,16 +592,24 @@ __global__ void __launch_bounds__(256, 2) ofdm_fft4096_kernel(const float2* __re
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int DEMOD>
-int launch_fft4096(const float2* x, float2* out, int nsym, const int* cp, const int* off, int len, int l_min, long long rows,
+template <int DEMOD, int R0>
+int launch_fft_r16(const float2* x, float2* out, int nsym, const int* cp, const int* off, int len, int l_min, long long rows,
                    int shift, cudaStream_t stream) {
-    const size_t smem = sizeof(float2) * ((size_t)kBigN + 256 + 2 * kBigPad);
-    auto kern = ofdm_fft4096_kernel<DEMOD>;
+    constexpr int N = 256 * R0, PAD = N + N / 16 + N / 256;
+    const size_t smem = sizeof(float2) * ((size_t)N + 256 + 2 * PAD);
+    auto kern = ofdm_fft_r16_kernel<DEMOD, R0>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long jobs = rows * nsym;
-    const int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * 2);
+    const int grid = (int)std::min<long long>(jobs, (long long)sb_num_sms() * (R0 == 16 ? 2 : 4));
     kern<<<grid, 256, smem, stream>>>(x, out, nsym, cp, off, len, l_min, rows, shift);
     return SB_OK;
+}
+
+template <int DEMOD>
+int launch_fft_pow2(int n, const float2* x, float2* out, int nsym, const int* cp, const int* off, int len, int l_min,
+                    long long rows, int shift, cudaStream_t stream) {
+    return n == 4096 ? launch_fft_r16<DEMOD, 16>(x, out, nsym, cp, off, len, l_min, rows, shift, stream)
+                     : launch_fft_r16<DEMOD, 8>(x, out, nsym, cp, off, len, l_min, rows, shift, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1262,9 +1288,9 @@ extern "C" int sb_ofdm_modulate(const float* d_x, float* d_out, int64_t rows, in
         SB_LAUNCH_CHECK();
         return SB_OK;
     }
-    if (fft_size == kBigN) {
-        int rc = launch_fft4096<0>((const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_out_off, out_len, 0, rows, shift,
-                                   (cudaStream_t)stream);
+    if (fft_size == 4096 || fft_size == 2048) {
+        int rc = launch_fft_pow2<0>(fft_size, (const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_out_off, out_len, 0, rows,
+                                    shift, (cudaStream_t)stream);
         if (rc) return rc;
         SB_LAUNCH_CHECK();
         return SB_OK;
@@ -1305,9 +1331,9 @@ extern "C" int sb_ofdm_demodulate(const float* d_x, float* d_out, int64_t rows, 
         SB_LAUNCH_CHECK();
         return SB_OK;
     }
-    if (fft_size == kBigN) {
-        int rc = launch_fft4096<1>((const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_in_off, in_len, l_min, rows, shift,
-                                   (cudaStream_t)stream);
+    if (fft_size == 4096 || fft_size == 2048) {
+        int rc = launch_fft_pow2<1>(fft_size, (const float2*)d_x, (float2*)d_out, num_symbols, d_cp, d_in_off, in_len, l_min, rows,
+                                    shift, (cudaStream_t)stream);
         if (rc) return rc;
         SB_LAUNCH_CHECK();
         return SB_OK;

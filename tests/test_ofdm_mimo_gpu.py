@@ -39,19 +39,21 @@ def test_ofdm_mod_demod_vs_oracle(cuda_device, n):
     assert OFDMDemodulator(n, 0, 5)(pad).shape == x.shape                   # trailing samples dropped
 
 
-def test_ofdm_4096_many_symbols_per_cta(cuda_device):
-    """4096-point grid with more OFDM symbols than resident CTAs: every CTA of the radix-16 kernel transforms several
-    symbols, so its cp.async prefetch of the next symbol into the second buffer is exercised (the per-size test above has
-    fewer symbols than CTAs). Oracle on the first and last frame, round trip on all."""
+@pytest.mark.parametrize("n", [4096, 2048])
+def test_ofdm_radix16_many_symbols_per_cta(cuda_device, n):
+    """4096- / 2048-point grids with more OFDM symbols than resident CTAs: every CTA of the in-place radix-16 kernel
+    transforms several symbols, so its cp.async prefetch of the next symbol into the second buffer is exercised (the
+    per-size test above has fewer symbols than CTAs). Oracle on the first and last frame, round trip on all."""
     from sionna_b200.phy.ofdm import OFDMModulator, OFDMDemodulator
-    rng = np.random.default_rng(4096)
-    n, cp = 4096, 288
-    x = _c64(rng, (48, 14, n))
+    rng = np.random.default_rng(n)
+    cp = 288 * n // 4096
+    x = _c64(rng, (48 * 4096 // n, 14, n))
     t = OFDMModulator(cp)(torch.from_numpy(x).to(cuda_device))
-    for r in (0, 47):
+    last = x.shape[0] - 1
+    for r in (0, last):
         np.testing.assert_allclose(t[r].cpu().numpy(), F.ofdm_modulate(x[r].astype(np.complex128), cp), atol=2e-4, rtol=1e-4)
     xh = OFDMDemodulator(n, -6, cp)(t)
-    for r in (0, 47):
+    for r in (0, last):
         np.testing.assert_allclose(xh[r].cpu().numpy(), F.ofdm_demodulate(F.ofdm_modulate(x[r].astype(np.complex128), cp), n, -6, cp),
                                    atol=3e-4, rtol=1e-4)
     assert np.abs(OFDMDemodulator(n, 0, cp)(t).cpu().numpy() - x).max() < 2e-4
