@@ -360,3 +360,32 @@ def test_frontend_tables_pusch_cdm_despreading(layers, ports, length, addpos, cd
     got = np.where(idx >= 0, w * yf[..., np.maximum(idx, 0)], 0).sum(-1)
     assert np.allclose(got, hr.reshape(2, 1, 2, ts, -1), atol=2e-6)
     assert np.allclose(t["e_sum"], np.maximum(er[0, 0, 0].reshape(ts, -1), 0).sum(0), rtol=1e-6)
+
+
+def test_fused_front_end_device_layout_lists_only_data_res():
+    """`FusedLSLinearDetector` hands the kernel a compacted RE list (resource elements that carry data for at least one
+    stream; pilot-only OFDM symbols are not walked) and term-major tables [streams, terms, listed REs]: the arrays it
+    uploads must be exactly that view of `frontend_tables` / the stream-management maps."""
+    from sionna_b200.phy.ofdm import ResourceGrid, LSChannelEstimator, FusedLSLinearDetector, frontend_tables
+    from sionna_b200.phy.ofdm.equalization import _sm_tables
+    from sionna_b200.phy.mimo import StreamManagement
+    rg = ResourceGrid(14, 76, 15e3, num_tx=1, num_streams_per_tx=2, cyclic_prefix_length=6, num_guard_carriers=(5, 6),
+                      dc_null=True, pilot_pattern="kronecker", pilot_ofdm_symbol_indices=[2, 11])
+    sm = StreamManagement(np.array([[1]]), 2)
+    est = LSChannelEstimator(rg, "lin")
+    fused = FusedLSLinearDetector(est, rg, sm, "maxlog", "qam", 4)
+    t = frontend_tables(rg, est)
+    _, _, _, data_pos = _sm_tables(rg, sm)
+    data_pos = np.asarray(data_pos)
+    keep = np.nonzero((data_pos >= 0).any(0))[0]
+    assert len(keep) == 12 * 64 == fused._num_listed                        # 2 of 14 symbols carry only pilots
+    d = fused._np
+    assert d["t_idx"].shape == (2, t["num_terms"], len(keep)) and d["t_idx"].flags["C_CONTIGUOUS"]
+    assert np.array_equal(d["t_idx"], t["t_idx"][:, keep, :].transpose(0, 2, 1))
+    assert np.array_equal(d["t_w"], t["t_w"][:, keep, :].transpose(0, 2, 1))
+    assert np.array_equal(d["re_full"], t["re_full"][keep]) and np.array_equal(d["e_sum"], t["e_sum"][keep])
+    assert np.array_equal(d["data_pos"], data_pos[:, keep]) and (d["data_pos"] >= 0).any(0).all()
+    # every stream's data symbols are all reachable through the list, each exactly once
+    for q in range(2):
+        assert np.array_equal(np.sort(d["data_pos"][q][d["data_pos"][q] >= 0]), np.arange(rg.pilot_pattern.num_data_symbols))
+    assert fused._lev[0].dtype == np.float32 and len(fused._lev[0]) == 4
