@@ -101,6 +101,11 @@ int sb_debug_phi(const float* d_x, float* d_scalar, float* d_packed, int64_t n, 
 int sb_ldpc_graph_on_chip(const sb_ldpc_graph* g);
 /* Bytes of device workspace `sb_ldpc_decode` needs for this graph (0 on the on-chip path). */
 size_t sb_ldpc_workspace_bytes(const sb_ldpc_graph* g);
+/* Test hook (no device needed): copies the host-side plan into caller arrays; any pointer may be NULL.
+ * dims[10] = {C, N, E, Lc, Lv, n_in, n_out, n_sub, n_active, flooding}; cn_order[C], vn_order[N], slot_of_edge[E],
+ * vn_slot[E], cn_off[Lc + 1], vn_off[Lv + 1]. */
+int sb_ldpc_graph_export(const sb_ldpc_graph* g, int32_t* dims, int32_t* cn_order, int32_t* vn_order,
+                         int32_t* slot_of_edge, int32_t* vn_slot, int32_t* cn_off, int32_t* vn_off);
 
 /* Decode `batch` codewords.
  *   d_llr    [batch, n_in]   channel logits log p(1)/p(0) (decoding.py:159-164); clipped to +-llr_max and

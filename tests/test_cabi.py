@@ -22,7 +22,7 @@ def test_header_symbols_exported_and_bound(sb_lib):
         assert hasattr(sb_lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in sionna_b200/_lib.py"
     for n in _lib.SIGNATURES:
-        assert n in names or n == "sb_ldpc_graph_export", f"{n} bound but not declared in the header"
+        assert n in names, f"{n} bound but not declared in the header"
 
 
 def test_error_codes_without_gpu(sb_lib):
