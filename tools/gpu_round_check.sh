@@ -27,6 +27,7 @@ cap frontend_pusch ofdm_frontend_kernel python bench.py --workload pusch --steps
 SKIP=0 cap cir_apply cir_apply_kernel python tools/pusch_sim.py --max-batches 1 --ebno-dbs 0 --global-batch 2048
 SKIP=0 cap lmmse_diag ofdm_lmmse_diag_kernel python tools/bench_phy_kernels.py --only ofdm_lmmse_4x16
 SKIP=0 cap fft76 ofdm_fft_small_kernel python tools/bench_phy_kernels.py --only ofdm_demodulate_76
+SKIP=1 cap fft4096 ofdm_fft_r16_kernel python tools/bench_phy_kernels.py --only ofdm_demodulate_4096
 ls -la gpurun_out/*.ncu-rep | wc -l
 # text summaries on the box (the .ncu-rep files come back too while they fit gpurun_out's 64 MiB)
 for f in gpurun_out/${R}_*.ncu-rep; do python tools/ncu_summary.py $f ${f%.ncu-rep}_ncu.txt > /dev/null 2>&1; done
