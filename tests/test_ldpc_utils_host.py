@@ -83,3 +83,38 @@ def test_weighted_bp_callback_scales_edges():
     assert torch.equal(cb(msg).flat_values, msg.flat_values)                # weights start at one
     cb.weights[:] = torch.tensor([0.5, 1.0, 2.0, 0.0, -1.0])
     np.testing.assert_allclose(cb(msg).flat_values.numpy(), vals * np.array([0.5, 1.0, 2.0, 0.0, -1.0], np.float32)[:, None])
+
+
+def test_j_function_and_inverse():
+    """fec/utils.py:184-267 (Brannstrom approximation): J(0+) = 0, J(inf) = 1, monotone, J^-1(J(mu)) = mu; the inverse is
+    clipped to 20 and both clip their arguments like the reference (1e-10 .. 1000, 1e-10 .. 1)."""
+    from sionna_b200.phy.fec.utils import j_fun, j_fun_inv
+    mu = np.array([1e-3, 0.1, 0.5, 1.0, 2.0, 4.0, 8.0, 15.0])
+    mi = j_fun(mu)
+    assert np.all(np.diff(mi) > 0) and mi[0] < 1e-3 and mi[-1] > 0.98 and j_fun(100.0) > 0.999999
+    np.testing.assert_allclose(j_fun_inv(mi), mu, rtol=1e-6)
+    h1, h2, h3 = 0.3073, 0.8935, 1.1064
+    np.testing.assert_allclose(j_fun(1.0), (1 - 2 ** (-h1 * 2.0 ** h2)) ** h3, rtol=1e-12)
+    assert j_fun(-5.0) == j_fun(1e-10) and j_fun(1e9) == j_fun(1000.0)
+    assert j_fun_inv(1.0) == 20.0 and j_fun_inv(2.0) == 20.0 and j_fun_inv(-1.0) == j_fun_inv(1e-10)
+
+
+def test_llr2mi_of_consistent_gaussian_llrs_follows_the_j_function():
+    """Logits (log p(1)/p(0)) of an all-zero codeword, ~ N(-mu, 2 mu): llr2mi estimates the mutual information that the
+    J-function approximates (fec/utils.py:116-182; the EXIT callback negates the decoder's internal messages, which use
+    the opposite sign, before the call)."""
+    from sionna_b200.phy.fec.utils import j_fun
+    rng = np.random.default_rng(5)
+    for mu in (0.5, 2.0, 6.0):
+        logits = torch.from_numpy(rng.normal(-mu, np.sqrt(2 * mu), size=400000).astype(np.float32))
+        mi = float(llr2mi(logits))
+        assert abs(mi - float(j_fun(mu))) < 0.01
+        signs = torch.from_numpy(rng.choice([-1.0, 1.0], size=logits.shape).astype(np.float32))
+        np.testing.assert_allclose(float(llr2mi(signs * logits, s=signs)), mi, rtol=1e-6)       # sign-adjusted variant
+    per_row = llr2mi(torch.zeros(3, 8), reduce_dims=False)
+    assert per_row.shape == (3,) and torch.allclose(per_row, torch.zeros(3))                    # llr = 0: no information
+    try:
+        llr2mi(torch.zeros(4, dtype=torch.int32))
+        assert False
+    except TypeError:
+        pass
