@@ -389,3 +389,49 @@ def test_fused_front_end_device_layout_lists_only_data_res():
     for q in range(2):
         assert np.array_equal(np.sort(d["data_pos"][q][d["data_pos"][q] >= 0]), np.arange(rg.pilot_pattern.num_data_symbols))
     assert fused._lev[0].dtype == np.float32 and len(fused._lev[0]) == 4
+
+
+def test_block_call_protocol_and_double_precision_fallback():
+    """Block.__call__ (reference block.py:82-155): float / complex arguments are cast to the block precision, ints and
+    Python scalars are left alone, build() runs once with the argument shapes; a block set to precision="double" keeps the
+    float64 / complex128 I/O contract while its call() sees single-precision tensors, and says so once per class. The
+    protocol is pure host logic, so a dummy block on the CPU device exercises it (kernels never run here)."""
+    import warnings
+    import torch
+    from sionna_b200.phy import config
+    from sionna_b200.phy.block import Block, PrecisionWarning
+
+    class Probe(Block):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.builds, self.seen = [], []
+
+        def build(self, *shapes, **kw_shapes):
+            self.builds.append((shapes, kw_shapes))
+
+        def call(self, x, idx, scale=None):
+            self.seen.append((x.dtype, idx.dtype, None if scale is None else scale.dtype, self.precision))
+            return x * 2, {"idx": idx, "z": x.to(torch.complex64) if not x.dtype.is_complex else x}
+
+    old = config._device
+    try:
+        config.device = "cpu"
+        p = Probe()
+        out, extra = p(np.ones((2, 3), np.float64), torch.arange(3), scale=torch.ones(3, dtype=torch.float64))
+        assert out.dtype == torch.float32 and p.seen[0] == (torch.float32, torch.int64, torch.float32, "single")
+        assert p.builds == [(((2, 3), (3,)), {"scale": (3,)})] and p.built
+        p(torch.ones(4, 3), torch.arange(3))
+        assert len(p.builds) == 1                                            # build() once
+        with pytest.raises(ValueError):
+            Probe(precision="half")
+        d = Probe(precision="double")
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            out, extra = d(torch.ones(2, 3, dtype=torch.float32), torch.arange(3))
+            d(torch.ones(2, 3), torch.arange(3))
+        assert sum(issubclass(i.category, PrecisionWarning) for i in w) <= 1  # once per class (0 if another test warned first)
+        assert d.seen[0][0] == torch.float32 and d.seen[0][3] == "single"     # call() ran in single precision ...
+        assert d.precision == "double" and d.rdtype == torch.float64          # ... and the block is double again afterwards
+        assert out.dtype == torch.float64 and extra["z"].dtype == torch.complex128 and extra["idx"].dtype == torch.int64
+    finally:
+        config._device = old
